@@ -1,0 +1,145 @@
+/* libvof -- C ABI of the B200-native 2-D/3-D VOF hot path (sm_100a CUDA kernels behind it).
+ *
+ * The reference (houkensjtu/taichi-2d-vof) has no FFI: its "interface" for the per-timestep
+ * path is (i) the zero-argument module-level kernels of 2dvof.py and the order the main loop
+ * calls them in (2dvof.py:513-528), (ii) the module-global fp32 fields of shape (nx+2, ny+2)
+ * (2dvof.py:53-89) read back with .to_numpy(), and (iii) the constants block 2dvof.py:19-50.
+ * Each entry below names the reference interface it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative VOF_E* code for argument/state errors,
+ *     or a positive cudaError_t; vof_last_error() gives a thread-local message.
+ *   - all compute entries are ASYNCHRONOUS on the context's stream (vof2d_set_stream);
+ *     only *_get / *_diagnostics / *_synchronize / *_step_host wait for the device.
+ *   - caller-visible arrays are the reference's logical (nx+2, ny+2) fp32, C order (j fastest).
+ *     On the device they live in a pitched allocation: element (i, j) of a field is
+ *     dev[i * pitch + j] with dev/pitch from vof2d_field_ptr (dev + 1 is 128-byte aligned).
+ *   - one context per (device, stream); a context is not re-entrant.
+ *   - there is NO CPU fallback: creation fails if no sm_100-class CUDA device is usable.
+ */
+#ifndef VOF_H_
+#define VOF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VOF_ABI_VERSION 1
+
+enum {
+    VOF_OK = 0,
+    VOF_EINVAL = -1,   /* bad argument */
+    VOF_ENODEV = -2,   /* no usable CUDA device (never falls back to the CPU) */
+    VOF_ENOMEM = -3,
+    VOF_ESTATE = -4    /* call not valid in this state (e.g. slab-only call on a full-domain ctx) */
+};
+
+/* Field ids: the live module-global fields of 2dvof.py:53-89 (scratch fields of the reference --
+ * mx1..my4, mxsum, mysum, magnitude, Ftd, ax, ay, cx, cy, rp, rm -- are never materialised). */
+enum {
+    VOF_F = 0,       /* 2dvof.py:53  volume fraction                      */
+    VOF_U = 1,       /* 2dvof.py:63  x-velocity on west faces             */
+    VOF_V = 2,       /* 2dvof.py:64  y-velocity on south faces            */
+    VOF_P = 3,       /* 2dvof.py:67  pressure                             */
+    VOF_RHO = 4,     /* 2dvof.py:71                                       */
+    VOF_NU = 5,      /* 2dvof.py:72  kinematic viscosity ("mu" in prose)  */
+    VOF_KAPPA = 6,   /* 2dvof.py:88                                       */
+    VOF_USTAR = 7,   /* 2dvof.py:65                                       */
+    VOF_VSTAR = 8,   /* 2dvof.py:66                                       */
+    VOF_W = 9,       /* 3dvof.py:88  (3-D contexts only)                  */
+    VOF_WSTAR = 10,  /* 3dvof.py:91  (3-D contexts only)                  */
+    VOF_FIELD_COUNT = 11
+};
+
+/* Constants block of 2dvof.py:19-50 / 3dvof.py:20-68.  Doubles, because the reference keeps them
+ * as Python scalars and folds sub-expressions in double before rounding once to fp32. */
+typedef struct VofParams {
+    int32_t nx, ny, nz;        /* interior cells; nz = 0 for 2-D                              */
+    double Lx, Ly, Lz;         /* 2dvof.py:22-23                                              */
+    double dx, dy, dz;         /* 2dvof.py:47-48; <= 0 -> derived the reference way from L/n  */
+    double dt;                 /* 2dvof.py:33                                                 */
+    double rho_l, rho_g;       /* 2dvof.py:24-25                                              */
+    double nu_l, nu_g;         /* 2dvof.py:26-27                                              */
+    double sigma;              /* 2dvof.py:28-29 (run-time field in the reference)            */
+    double gx, gy, gz;         /* 2dvof.py:30-31                                              */
+    int32_t n_jacobi;          /* 2dvof.py:521 (10)                                           */
+    /* Row-slab decomposition along i (new capability; the reference is single-address-space).
+     * Full domain: slab_lo = 1, slab_hi = nx, halo = 1 (or all three 0 = same thing).         */
+    int32_t slab_lo, slab_hi;  /* global interior rows owned by this context                  */
+    int32_t halo;              /* ghost rows kept each side (>= 1); >= VOF_SLAB_MIN_HALO for slabs */
+    int32_t device;            /* CUDA device ordinal, -1 = current                           */
+} VofParams;
+
+#define VOF_SLAB_MIN_HALO 13   /* dependency radius of one whole step along i       */
+
+/* vof2d_step / vof2d_run flags */
+#define VOF_STEP_MATERIALIZE_PROPS 1u  /* also write rho, nu (they are derived state: 2dvof.py:198-203) */
+#define VOF_STEP_NO_FUSION         2u  /* run the reference's kernel sequence one entry at a time       */
+
+typedef struct VofCtx VofCtx;
+
+const char* vof_last_error(void);
+int vof_abi_version(void);
+void vof_default_params(VofParams* p);          /* the reference's constants, 2dvof.py:19-34 */
+
+/* ---- lifetime (replaces: ti.init + field allocation, 2dvof.py:9, 53-89) ---- */
+size_t vof2d_arena_bytes(const VofParams* p);   /* device bytes vof2d_create needs            */
+int vof2d_create(const VofParams* p, VofCtx** out);
+/* as above but carving the fields out of caller-owned device memory (e.g. a torch /
+ * symmetric-memory allocation); arena must be 256-byte aligned and >= vof2d_arena_bytes */
+int vof2d_create_in(const VofParams* p, void* arena, size_t arena_bytes, VofCtx** out);
+int vof2d_destroy(VofCtx* c);
+int vof2d_set_stream(VofCtx* c, void* cuda_stream);
+int vof2d_synchronize(VofCtx* c);
+int vof2d_get_params(const VofCtx* c, VofParams* out);   /* with dx/dy as resolved */
+
+/* ---- one entry per reference kernel, same observable effect on the live fields ---- */
+int vof2d_set_init_F(VofCtx* c, int ic);        /* 2dvof.py:137-159 (+find_area 102-134)      */
+int vof2d_set_BC(VofCtx* c);                    /* 2dvof.py:162-189                           */
+int vof2d_cal_nu_rho(VofCtx* c);                /* 2dvof.py:198-203                           */
+int vof2d_get_normal_young(VofCtx* c);          /* 2dvof.py:283-309                           */
+int vof2d_advect_upwind(VofCtx* c);             /* 2dvof.py:206-233                           */
+int vof2d_solve_p_jacobi(VofCtx* c, int nsweeps);/* 2dvof.py:236-266, nsweeps calls in one    */
+int vof2d_update_uv(VofCtx* c);                 /* 2dvof.py:269-280                           */
+int vof2d_fct_x_sweep(VofCtx* c);               /* 2dvof.py:321-382                           */
+int vof2d_fct_y_sweep(VofCtx* c);               /* 2dvof.py:385-448                           */
+int vof2d_solve_VOF_rudman(VofCtx* c, int istep);/* 2dvof.py:312-318                          */
+int vof2d_post_process_f(VofCtx* c);            /* 2dvof.py:452-455                           */
+
+/* ---- the loop body 2dvof.py:513-528 as one call (fused kernels, same result) ---- */
+int vof2d_step(VofCtx* c, int istep, unsigned flags);
+/* steps istep0 .. istep0+nsteps-1 back to back (CUDA-graph replay for small grids) */
+int vof2d_run(VofCtx* c, int istep0, int nsteps, unsigned flags);
+/* host-buffer form: H2D of u,v,p,F (each (nx+2)*(ny+2) floats), one step, D2H of u,v,p,F.
+ * Synchronous.  Any pointer may be NULL to skip that transfer. */
+int vof2d_step_host(VofCtx* c, int istep, unsigned flags,
+                    const float* u_in, const float* v_in, const float* p_in, const float* F_in,
+                    float* u_out, float* v_out, float* p_out, float* F_out);
+
+/* ---- field access (replaces: field.to_numpy()/from_numpy(), 2dvof.py:535, 565) ---- */
+int vof2d_field_ptr(VofCtx* c, int field, float** dev, int64_t* pitch_elems, int64_t* rows);
+int vof2d_field_get(VofCtx* c, int field, float* host_dst);        /* logical rows of this ctx */
+int vof2d_field_set(VofCtx* c, int field, const float* host_src);
+int vof2d_field_fill(VofCtx* c, int field, float value);
+
+/* ---- diagnostics (new; the reference only prints on Courant violation, 2dvof.py:274-280) ----
+ * mass = sum F over owned interior cells (fp64), max_cfl = max(|u|dt/dx, |v|dt/dy),
+ * residual = L-inf of (rhs - A p) over owned interior cells, courant_count = number of faces
+ * with u*dt > 0.25*dx (the reference's print condition).  Any pointer may be NULL.  Synchronous. */
+int vof2d_diagnostics(VofCtx* c, double* mass, float* max_cfl, float* residual, int64_t* courant_count);
+
+/* ---- slabs (new): halo rows are contiguous runs of `pitch` floats.  Pack/unpack the rows the
+ * neighbours need; the transport (NVLink P2P / NCCL) is the caller's.  side: 0 = lower i, 1 = upper. */
+int vof2d_halo_rows(const VofCtx* c, int* rows_per_side, int64_t* floats_per_field_side);
+int vof2d_halo_ptr(VofCtx* c, int field, int side, int send, float** dev, int64_t* count);
+/* direct peer push: write my boundary rows into the neighbour's halo rows (peer-mapped memory) */
+int vof2d_halo_push(VofCtx* c, int field, int side, float* peer_halo_dst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOF_H_ */

@@ -1,0 +1,115 @@
+"""ctypes binding of libvof.so (the C ABI declared in include/vof.h).
+
+There is NO CPU fallback: if the shared library is missing this module raises, and
+``vof2d_create`` itself fails without an sm_100-class CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvof.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+# field ids (include/vof.h)
+VOF_F, VOF_U, VOF_V, VOF_P, VOF_RHO, VOF_NU, VOF_KAPPA, VOF_USTAR, VOF_VSTAR, VOF_W, VOF_WSTAR = range(11)
+FIELD_IDS = {"F": VOF_F, "u": VOF_U, "v": VOF_V, "p": VOF_P, "rho": VOF_RHO, "nu": VOF_NU,
+             "kappa": VOF_KAPPA, "u_star": VOF_USTAR, "v_star": VOF_VSTAR, "w": VOF_W, "w_star": VOF_WSTAR}
+VOF_STEP_MATERIALIZE_PROPS = 1
+VOF_STEP_NO_FUSION = 2
+VOF_SLAB_MIN_HALO = 13
+
+
+class VofParams(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
+                ("Lx", C.c_double), ("Ly", C.c_double), ("Lz", C.c_double),
+                ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
+                ("dt", C.c_double),
+                ("rho_l", C.c_double), ("rho_g", C.c_double),
+                ("nu_l", C.c_double), ("nu_g", C.c_double),
+                ("sigma", C.c_double),
+                ("gx", C.c_double), ("gy", C.c_double), ("gz", C.c_double),
+                ("n_jacobi", C.c_int32),
+                ("slab_lo", C.c_int32), ("slab_hi", C.c_int32), ("halo", C.c_int32),
+                ("device", C.c_int32)]
+
+
+class VofError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libvof error {code}: {msg}")
+        self.code = code
+
+
+def build(force: bool = False) -> str:
+    """Compile libvof.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "vof.h")]
+    stale = (not os.path.exists(LIB_PATH)
+             or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs if os.path.exists(s)))
+    if force or stale:
+        subprocess.run(["make", "-C", CSRC, "-s"] + (["-B"] if force else []), check=True)
+    return LIB_PATH
+
+
+_LIB = None
+
+# every symbol include/vof.h declares: name -> (restype, argtypes)
+_P = C.POINTER
+_ctx = C.c_void_p
+SIGNATURES = {
+    "vof_last_error": (C.c_char_p, []),
+    "vof_abi_version": (C.c_int, []),
+    "vof_default_params": (None, [_P(VofParams)]),
+    "vof2d_arena_bytes": (C.c_size_t, [_P(VofParams)]),
+    "vof2d_create": (C.c_int, [_P(VofParams), _P(_ctx)]),
+    "vof2d_create_in": (C.c_int, [_P(VofParams), C.c_void_p, C.c_size_t, _P(_ctx)]),
+    "vof2d_destroy": (C.c_int, [_ctx]),
+    "vof2d_set_stream": (C.c_int, [_ctx, C.c_void_p]),
+    "vof2d_synchronize": (C.c_int, [_ctx]),
+    "vof2d_get_params": (C.c_int, [_ctx, _P(VofParams)]),
+    "vof2d_set_init_F": (C.c_int, [_ctx, C.c_int]),
+    "vof2d_set_BC": (C.c_int, [_ctx]),
+    "vof2d_cal_nu_rho": (C.c_int, [_ctx]),
+    "vof2d_get_normal_young": (C.c_int, [_ctx]),
+    "vof2d_advect_upwind": (C.c_int, [_ctx]),
+    "vof2d_solve_p_jacobi": (C.c_int, [_ctx, C.c_int]),
+    "vof2d_update_uv": (C.c_int, [_ctx]),
+    "vof2d_fct_x_sweep": (C.c_int, [_ctx]),
+    "vof2d_fct_y_sweep": (C.c_int, [_ctx]),
+    "vof2d_solve_VOF_rudman": (C.c_int, [_ctx, C.c_int]),
+    "vof2d_post_process_f": (C.c_int, [_ctx]),
+    "vof2d_step": (C.c_int, [_ctx, C.c_int, C.c_uint]),
+    "vof2d_run": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_uint]),
+    "vof2d_step_host": (C.c_int, [_ctx, C.c_int, C.c_uint] + [C.c_void_p] * 8),
+    "vof2d_field_ptr": (C.c_int, [_ctx, C.c_int, _P(C.c_void_p), _P(C.c_int64), _P(C.c_int64)]),
+    "vof2d_field_get": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
+    "vof2d_field_set": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
+    "vof2d_field_fill": (C.c_int, [_ctx, C.c_int, C.c_float]),
+    "vof2d_diagnostics": (C.c_int, [_ctx, _P(C.c_double), _P(C.c_float), _P(C.c_float), _P(C.c_int64)]),
+    "vof2d_halo_rows": (C.c_int, [_ctx, _P(C.c_int), _P(C.c_int64)]),
+    "vof2d_halo_ptr": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _P(C.c_void_p), _P(C.c_int64)]),
+    "vof2d_halo_push": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p]),
+}
+
+
+def lib():
+    """Load libvof.so.  Raises (never degrades to a CPU path) if it is absent."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(libvof is CUDA-only; there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)   # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(rc: int):
+    if rc != 0:
+        raise VofError(rc, lib().vof_last_error().decode("utf-8", "replace"))

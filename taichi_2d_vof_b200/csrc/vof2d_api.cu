@@ -1,0 +1,641 @@
+// libvof C ABI (include/vof.h) -- 2-D context, launches, field access, diagnostics.
+// Host code only decides ranges and launch shapes; all arithmetic is in vof2d_kernels.cuh.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "vof2d_kernels.cuh"
+
+using namespace vof;
+
+// ------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                             \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail((int)e_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define CHECK_CTX(c) \
+    do { if (!(c)) return fail(VOF_EINVAL, "null context"); } while (0)
+
+extern "C" const char* vof_last_error(void) { return g_err; }
+extern "C" int vof_abi_version(void) { return VOF_ABI_VERSION; }
+
+extern "C" void vof_default_params(VofParams* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->nx = 200; p->ny = 200; p->nz = 0;                 // 2dvof.py:19-20
+    p->Lx = 0.1; p->Ly = 0.1; p->Lz = 0.1;               // 2dvof.py:22-23
+    p->dx = p->dy = p->dz = 0.0;                         // derive the reference way
+    p->dt = 4e-6;                                        // 2dvof.py:33
+    p->rho_l = 1000.0; p->rho_g = 50.0;                  // 2dvof.py:24-25
+    p->nu_l = 1.0e-6; p->nu_g = 1.5e-5;                  // 2dvof.py:26-27
+    p->sigma = 0.007;                                    // 2dvof.py:29
+    p->gx = 0; p->gy = -5; p->gz = 0;                    // 2dvof.py:30-31
+    p->n_jacobi = 10;                                    // 2dvof.py:521
+    p->slab_lo = 0; p->slab_hi = 0; p->halo = 0; p->device = -1;
+}
+
+// ------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------
+enum { BUF_F0 = 0, BUF_F1, BUF_U, BUF_V, BUF_P0, BUF_P1, BUF_US, BUF_VS, BUF_RHS, BUF_KAPPA, BUF_RHO, BUF_NU, BUF_COUNT };
+
+struct VofCtx {
+    VofParams P;
+    Grid g;
+    Consts k;
+    InitConsts ic2, ic3, ic1;
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    bool own_arena;
+    char* arena;
+    size_t arena_bytes, field_bytes;
+    float* buf[BUF_COUNT];     // pointers to logical (row 0, j = 0)
+    int F_cur, p_cur;          // which of the ping-pong buffers is live
+    float *xs, *ys;            // node coordinates (fp32), 2dvof.py:41-46
+    Diag* diag;                // device
+    bool rhs_valid;
+    int lo, hi, H;             // owned global interior rows, halo depth
+    bool has_lo, has_hi;       // this context holds the physical wall at i = 1 / i = nx
+    // local row ranges (inclusive)
+    int all_a, all_b;          // rows whose global index is in [0, nx+1]
+    int in_a, in_b;            // rows whose global index is in [1, nx]
+    // CUDA graphs of two consecutive steps, keyed by parity of the first istep and flags
+    cudaGraphExec_t graph[2][4];
+    float* F() { return buf[F_cur ? BUF_F1 : BUF_F0]; }
+    float* F_alt() { return buf[F_cur ? BUF_F0 : BUF_F1]; }
+    float* p() { return buf[p_cur ? BUF_P1 : BUF_P0]; }
+    float* p_alt() { return buf[p_cur ? BUF_P0 : BUF_P1]; }
+};
+
+static size_t field_stride_bytes(int nrows, int pitch) {
+    size_t b = (size_t)nrows * pitch * sizeof(float);
+    return (b + 255) / 256 * 256;
+}
+
+static int resolve(const VofParams* in, VofParams* P, Grid* g, int* lo, int* hi, int* H) {
+    if (!in) return fail(VOF_EINVAL, "null params");
+    *P = *in;
+    if (P->nx < 4 || P->ny < 4) return fail(VOF_EINVAL, "nx, ny must be >= 4 (got %d x %d)", P->nx, P->ny);
+    if (P->nz != 0) return fail(VOF_EINVAL, "vof2d_* needs nz == 0 (use vof3d_* for 3-D)");
+    if (!(P->Lx > 0) || !(P->Ly > 0) || !(P->dt > 0)) return fail(VOF_EINVAL, "Lx, Ly, dt must be positive");
+    if (P->n_jacobi < 0) return fail(VOF_EINVAL, "n_jacobi must be >= 0");
+    if (P->slab_lo == 0 && P->slab_hi == 0) { P->slab_lo = 1; P->slab_hi = P->nx; }
+    if (P->halo == 0) P->halo = 1;
+    if (P->slab_lo < 1 || P->slab_hi > P->nx || P->slab_lo > P->slab_hi)
+        return fail(VOF_EINVAL, "slab rows [%d, %d] outside [1, %d]", P->slab_lo, P->slab_hi, P->nx);
+    const bool full = (P->slab_lo == 1 && P->slab_hi == P->nx);
+    if (!full) {
+        const int need = P->n_jacobi + 3;
+        if (P->halo < need) return fail(VOF_EINVAL, "slab halo %d < n_jacobi + 3 = %d", P->halo, need);
+        if (P->slab_hi - P->slab_lo + 1 < P->halo)
+            return fail(VOF_EINVAL, "slab of %d rows is thinner than its halo %d", P->slab_hi - P->slab_lo + 1, P->halo);
+    }
+    if (P->halo < 1) return fail(VOF_EINVAL, "halo must be >= 1");
+    *lo = P->slab_lo; *hi = P->slab_hi; *H = P->halo;
+    g->nx = P->nx; g->ny = P->ny;
+    g->gi0 = *lo - *H;
+    g->nrows = (*hi - *lo + 1) + 2 * *H;
+    g->pitch = round_up(kColOff + P->ny + 2, kPitchAlign);
+    return VOF_OK;
+}
+
+extern "C" size_t vof2d_arena_bytes(const VofParams* p) {
+    VofParams P; Grid g{}; int lo = 0, hi = 0, H = 0;
+    if (resolve(p, &P, &g, &lo, &hi, &H) != VOF_OK) return 0;
+    size_t xy = ((size_t)(P.nx + 3 + P.ny + 3) * sizeof(float) + 255) / 256 * 256;
+    return field_stride_bytes(g.nrows, g.pitch) * BUF_COUNT + xy + 256;
+}
+
+static void node_coords(std::vector<float>& x, int n, double L) {
+    // np.hstack((0.0, np.linspace(0, L, n + 1), L)).astype(float32), 2dvof.py:43-46
+    x.assign((size_t)n + 3, 0.0f);
+    const double step = L / n;
+    for (int k = 0; k <= n; ++k) x[(size_t)k + 1] = (float)(k == n ? L : k * step);
+    x[0] = 0.0f;
+    x[(size_t)n + 2] = (float)L;
+}
+
+static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, VofCtx** out) {
+    if (!out) return fail(VOF_EINVAL, "null out pointer");
+    *out = nullptr;
+    VofParams P; Grid g{}; int lo = 0, hi = 0, H = 0;
+    int rc = resolve(in, &P, &g, &lo, &hi, &H);
+    if (rc != VOF_OK) return rc;
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(VOF_ENODEV, "no CUDA device (%s); libvof has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    int dev = P.device;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(VOF_EINVAL, "device %d out of range (%d devices)", dev, ndev);
+    CU(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail(VOF_ENODEV, "device %d is sm_%d%d; libvof is built for sm_100a only", dev, prop.major, prop.minor);
+
+    VofCtx* c = new (std::nothrow) VofCtx();
+    if (!c) return fail(VOF_ENOMEM, "out of host memory");
+    memset(c, 0, sizeof(*c));
+    c->device = dev;
+    c->lo = lo; c->hi = hi; c->H = H;
+    c->has_lo = (lo == 1); c->has_hi = (hi == P.nx);
+    c->g = g;
+
+    // node coordinates and dx, dy (2dvof.py:41-50)
+    std::vector<float> x, y;
+    node_coords(x, P.nx, P.Lx);
+    node_coords(y, P.ny, P.Ly);
+    if (!(P.dx > 0)) P.dx = (double)x[3] - (double)x[2];
+    if (!(P.dy > 0)) P.dy = (double)y[3] - (double)y[2];
+    c->P = P;
+    const double dx = P.dx, dy = P.dy, dxi = 1 / dx, dyi = 1 / dy;
+    Consts& k = c->k;
+    k.dt = (float)P.dt; k.dx = (float)dx; k.dy = (float)dy; k.dxi = (float)dxi; k.dyi = (float)dyi;
+    k.dxi2 = (float)(dxi * dxi); k.dyi2 = (float)(dyi * dyi);
+    k.dxdy = (float)(dx * dy); k.dtdy = (float)(P.dt * dy); k.dtdx = (float)(P.dt * dx);
+    k.m1_2dx = (float)(-1 / (2 * dx)); k.m1_2dy = (float)(-1 / (2 * dy));
+    k.i_dx_2 = (float)(1 / dx / 2); k.i_dy_2 = (float)(1 / dy / 2);
+    k.neg_sigma = -(float)P.sigma;
+    k.rho_l = (float)P.rho_l; k.rho_g = (float)P.rho_g; k.nu_l = (float)P.nu_l; k.nu_g = (float)P.nu_g;
+    k.gx = (float)P.gx; k.gy = (float)P.gy;
+    k.cflx = (float)(0.25 * dx); k.cfly = (float)(0.25 * dy);
+    // initial-condition constants (2dvof.py:141-158)
+    InitConsts ic{};
+    ic.hdx = (float)(dx / 2); ic.hdy = (float)(dy / 2); ic.sqrt2dx = (float)(std::sqrt(2.0) * dx);
+    ic.x2 = (float)(P.Lx / 3); ic.y2 = (float)(P.Ly / 2);
+    ic.r = (float)(P.Lx / 12); ic.cx = (float)(P.Lx / 2);
+    ic.ycut = (float)(P.Ly * 0.37);
+    c->ic1 = ic;
+    c->ic2 = ic; c->ic2.cy = 2.0f * ic.r;                 // cy = 2 * r in fp32 (r is a kernel local)
+    c->ic3 = ic; c->ic3.cy = (float)P.Ly - 3.0f * ic.r;   // Ly - 3 * r in fp32
+
+    c->all_a = std::max(0, -g.gi0);
+    c->all_b = std::min(g.nrows - 1, P.nx + 1 - g.gi0);
+    c->in_a = std::max(0, 1 - g.gi0);
+    c->in_b = std::min(g.nrows - 1, P.nx - g.gi0);
+
+    const size_t need = vof2d_arena_bytes(&P);
+    c->field_bytes = field_stride_bytes(g.nrows, g.pitch);
+    if (arena) {
+        if (((uintptr_t)arena & 255) != 0) { delete c; return fail(VOF_EINVAL, "arena must be 256-byte aligned"); }
+        if (arena_bytes < need) { delete c; return fail(VOF_EINVAL, "arena too small: %zu < %zu", arena_bytes, need); }
+        c->arena = (char*)arena; c->own_arena = false;
+    } else {
+        e = cudaMalloc((void**)&c->arena, need);
+        if (e != cudaSuccess) { delete c; return fail(VOF_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", need, cudaGetErrorString(e)); }
+        c->own_arena = true;
+    }
+    c->arena_bytes = need;
+    e = cudaMemset(c->arena, 0, need);   // the reference's fields start at zero (2dvof.py:53-89)
+    if (e != cudaSuccess) { if (c->own_arena) cudaFree(c->arena); delete c; return fail((int)e, "cudaMemset failed: %s", cudaGetErrorString(e)); }
+    for (int b = 0; b < BUF_COUNT; ++b) c->buf[b] = (float*)(c->arena + c->field_bytes * b) + kColOff;
+    c->xs = (float*)(c->arena + c->field_bytes * BUF_COUNT);
+    c->ys = c->xs + (P.nx + 3);
+    c->diag = (Diag*)(c->arena + need - 256);
+    CU(cudaMemcpy(c->xs, x.data(), x.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->ys, y.data(), y.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    *out = c;
+    return VOF_OK;
+}
+
+extern "C" int vof2d_create(const VofParams* p, VofCtx** out) { return create_impl(p, nullptr, 0, out); }
+extern "C" int vof2d_create_in(const VofParams* p, void* arena, size_t arena_bytes, VofCtx** out) {
+    if (!arena) return fail(VOF_EINVAL, "null arena");
+    return create_impl(p, arena, arena_bytes, out);
+}
+
+extern "C" int vof2d_destroy(VofCtx* c) {
+    if (!c) return VOF_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 4; ++b)
+            if (c->graph[a][b]) cudaGraphExecDestroy(c->graph[a][b]);
+    if (c->own_arena && c->arena) cudaFree(c->arena);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);   // a caller-provided stream is left alone
+    delete c;
+    return VOF_OK;
+}
+
+extern "C" int vof2d_set_stream(VofCtx* c, void* cuda_stream) {
+    CHECK_CTX(c);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 4; ++b)
+            if (c->graph[a][b]) { cudaGraphExecDestroy(c->graph[a][b]); c->graph[a][b] = nullptr; }
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    return VOF_OK;
+}
+
+extern "C" int vof2d_synchronize(VofCtx* c) {
+    CHECK_CTX(c);
+    CU(cudaStreamSynchronize(c->stream));
+    return VOF_OK;
+}
+
+extern "C" int vof2d_get_params(const VofCtx* c, VofParams* out) {
+    CHECK_CTX(c);
+    if (!out) return fail(VOF_EINVAL, "null out");
+    *out = c->P;
+    return VOF_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static int launch_ok(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return VOF_OK;
+}
+constexpr int kRowsPerBlock = 32;   // rows marched by one block of the streaming kernels
+constexpr int kFctRows = 64;        // x-sweep chunk (6 warm-up rows are re-read per chunk)
+
+static unsigned bc_mask_all = 31u;
+
+static int run_set_bc(VofCtx* c, unsigned mask) {
+    const int nA = c->all_b - c->all_a + 1;
+    const int nB = c->g.ny + 2;
+    const int n = nA + (c->has_lo ? nB : 0) + (c->has_hi ? nB : 0);
+    k_set_bc<<<cdiv(n, 128), 128, 0, c->stream>>>(c->g, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->p(), c->buf[BUF_RHO],
+                                                   c->all_a, c->all_b, c->has_lo, c->has_hi, mask);
+    return launch_ok("k_set_bc");
+}
+
+static int run_cal_nu_rho(VofCtx* c) {
+    const int rows = c->all_b - c->all_a + 1;
+    dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, kRowsPerBlock));
+    k_cal_nu_rho<<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_RHO], c->buf[BUF_NU], c->all_a, c->all_b, kRowsPerBlock);
+    return launch_ok("k_cal_nu_rho");
+}
+
+static int run_kappa(VofCtx* c) {
+    constexpr int TI = 16, TJ = 64;
+    const int rows = c->in_b - c->in_a + 1;
+    dim3 grid(cdiv(c->g.ny, TJ), cdiv(rows, TI));
+    k_kappa<TI, TJ><<<grid, 256, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_KAPPA], c->in_a, c->in_b);
+    return launch_ok("k_kappa");
+}
+
+static int run_advect(VofCtx* c, bool inline_props) {
+    const int a = std::max(c->in_a, 1), b = std::min(c->in_b, c->g.nrows - 2);
+    const int rows = b - a + 1;
+    dim3 grid(cdiv(c->g.ny, kBlockJ), cdiv(rows, kRowsPerBlock));
+    if (inline_props)
+        k_advect<true><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->buf[BUF_KAPPA], nullptr,
+                                                       nullptr, c->buf[BUF_US], c->buf[BUF_VS], a, b, kRowsPerBlock);
+    else
+        k_advect<false><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->buf[BUF_KAPPA],
+                                                        c->buf[BUF_RHO], c->buf[BUF_NU], c->buf[BUF_US], c->buf[BUF_VS], a, b, kRowsPerBlock);
+    return launch_ok("k_advect");
+}
+
+static int run_rhs(VofCtx* c, bool inline_props) {
+    const int a = c->in_a, b = std::min(c->in_b, c->g.nrows - 2);
+    const int rows = b - a + 1;
+    dim3 grid(cdiv(c->g.ny, kBlockJ), cdiv(rows, kRowsPerBlock));
+    if (inline_props)
+        k_rhs<true><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_RHS], a, b, kRowsPerBlock);
+    else
+        k_rhs<false><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->buf[BUF_RHO], c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_RHS], a, b, kRowsPerBlock);
+    c->rhs_valid = true;
+    return launch_ok("k_rhs");
+}
+
+// one sweep, rhs_mode as in k_jacobi
+static int run_jacobi_sweep(VofCtx* c, int rhs_mode) {
+    const int rows = c->all_b - c->all_a + 1;
+    dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, kRowsPerBlock));
+    const float* rhoF = rhs_mode == 2 ? c->F() : c->buf[BUF_RHO];
+#define JARGS c->g, c->k, c->p(), c->p_alt(), c->buf[BUF_RHS], rhoF, c->buf[BUF_US], c->buf[BUF_VS], c->all_a, c->all_b, kRowsPerBlock
+    if (rhs_mode == 0) k_jacobi<0><<<grid, kBlockJ, 0, c->stream>>>(JARGS);
+    else if (rhs_mode == 1) k_jacobi<1><<<grid, kBlockJ, 0, c->stream>>>(JARGS);
+    else k_jacobi<2><<<grid, kBlockJ, 0, c->stream>>>(JARGS);
+#undef JARGS
+    c->p_cur ^= 1;
+    return launch_ok("k_jacobi");
+}
+
+static int run_project(VofCtx* c, bool inline_props) {
+    const int a = std::max(c->in_a, 1), b = c->in_b;
+    const int rows = b - a + 1;
+    dim3 grid(cdiv(c->g.ny, kBlockJ), cdiv(rows, kRowsPerBlock));
+    unsigned long long* cc = &c->diag->courant_count;
+    CU(cudaMemsetAsync(cc, 0, sizeof(*cc), c->stream));
+    if (inline_props)
+        k_project<true><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->p(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_U], c->buf[BUF_V], cc, a, b, kRowsPerBlock);
+    else
+        k_project<false><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->buf[BUF_RHO], c->p(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_U], c->buf[BUF_V], cc, a, b, kRowsPerBlock);
+    return launch_ok("k_project");
+}
+
+static int run_fct_x(VofCtx* c, bool post) {
+    const int rows = c->in_b - c->in_a + 1;
+    dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, kFctRows));
+    if (post) k_fct_x<true><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, kFctRows);
+    else k_fct_x<false><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, kFctRows);
+    c->F_cur ^= 1;
+    return launch_ok("k_fct_x");
+}
+
+static int run_fct_y(VofCtx* c, bool post) {
+    constexpr int TR = 4, TJ = 256;
+    const int rows = c->all_b - c->all_a + 1;
+    dim3 grid(cdiv(c->g.ny, TJ), cdiv(rows, TR));
+    if (post) k_fct_y<true, TR, TJ><<<grid, 256, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b);
+    else k_fct_y<false, TR, TJ><<<grid, 256, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b);
+    c->F_cur ^= 1;
+    return launch_ok("k_fct_y");
+}
+
+static int run_post(VofCtx* c) {
+    const int rows = c->all_b - c->all_a + 1;
+    dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, kRowsPerBlock));
+    k_post_process_f<<<grid, kBlockJ, 0, c->stream>>>(c->g, c->F(), c->all_a, c->all_b, kRowsPerBlock);
+    return launch_ok("k_post_process_f");
+}
+
+#define TRY(x) do { int rc_ = (x); if (rc_ != VOF_OK) return rc_; } while (0)
+
+// ------------------------------------------------------------------------------------
+// one entry per reference kernel
+// ------------------------------------------------------------------------------------
+extern "C" int vof2d_set_init_F(VofCtx* c, int ic) {
+    CHECK_CTX(c);
+    if (ic < 1 || ic > 3) return fail(VOF_EINVAL, "ic must be 1, 2 or 3 (got %d)", ic);
+    const InitConsts& k = ic == 1 ? c->ic1 : (ic == 2 ? c->ic2 : c->ic3);
+    const int rows = c->all_b - c->all_a + 1;
+    dim3 grid(cdiv(c->g.ny + 2, kBlockJ), std::min(rows, 1024));
+    k_set_init_F<<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, k, ic, c->xs, c->ys, c->F(), c->all_a, c->all_b);
+    return launch_ok("k_set_init_F");
+}
+extern "C" int vof2d_set_BC(VofCtx* c) { CHECK_CTX(c); return run_set_bc(c, bc_mask_all); }
+extern "C" int vof2d_cal_nu_rho(VofCtx* c) { CHECK_CTX(c); return run_cal_nu_rho(c); }
+extern "C" int vof2d_get_normal_young(VofCtx* c) { CHECK_CTX(c); return run_kappa(c); }
+extern "C" int vof2d_advect_upwind(VofCtx* c) { CHECK_CTX(c); c->rhs_valid = false; return run_advect(c, false); }
+
+extern "C" int vof2d_solve_p_jacobi(VofCtx* c, int nsweeps) {
+    CHECK_CTX(c);
+    if (nsweeps < 0) return fail(VOF_EINVAL, "nsweeps must be >= 0");
+    if (nsweeps == 1) return run_jacobi_sweep(c, 1);   // the reference's structure: rhs recomputed inside the sweep
+    if (nsweeps == 0) return VOF_OK;
+    TRY(run_rhs(c, false));
+    for (int s = 0; s < nsweeps; ++s) TRY(run_jacobi_sweep(c, 0));
+    return VOF_OK;
+}
+extern "C" int vof2d_update_uv(VofCtx* c) { CHECK_CTX(c); return run_project(c, false); }
+extern "C" int vof2d_fct_x_sweep(VofCtx* c) { CHECK_CTX(c); return run_fct_x(c, false); }
+extern "C" int vof2d_fct_y_sweep(VofCtx* c) { CHECK_CTX(c); return run_fct_y(c, false); }
+extern "C" int vof2d_solve_VOF_rudman(VofCtx* c, int istep) {
+    CHECK_CTX(c);
+    if (istep % 2 == 0) { TRY(run_fct_y(c, false)); TRY(run_fct_x(c, false)); }
+    else { TRY(run_fct_x(c, false)); TRY(run_fct_y(c, false)); }
+    return VOF_OK;
+}
+extern "C" int vof2d_post_process_f(VofCtx* c) { CHECK_CTX(c); return run_post(c); }
+
+// ------------------------------------------------------------------------------------
+// the loop body 2dvof.py:513-528
+// ------------------------------------------------------------------------------------
+static int step_impl(VofCtx* c, int istep, unsigned flags) {
+    if (flags & VOF_STEP_NO_FUSION) {
+        TRY(run_cal_nu_rho(c));                                   // 513
+        TRY(run_kappa(c));                                        // 514
+        c->rhs_valid = false;
+        TRY(run_advect(c, false));                                // 517
+        TRY(run_set_bc(c, bc_mask_all));                          // 518
+        for (int s = 0; s < c->P.n_jacobi; ++s) TRY(run_jacobi_sweep(c, 1));   // 521-522
+        TRY(run_project(c, false));                               // 524
+        TRY(run_set_bc(c, bc_mask_all));                          // 525
+        if (istep % 2 == 0) { TRY(run_fct_y(c, false)); TRY(run_fct_x(c, false)); }   // 526
+        else { TRY(run_fct_x(c, false)); TRY(run_fct_y(c, false)); }
+        TRY(run_post(c));                                         // 527
+        TRY(run_set_bc(c, bc_mask_all));                          // 528
+        return VOF_OK;
+    }
+    const bool props = (flags & VOF_STEP_MATERIALIZE_PROPS) != 0;
+    const unsigned mask = props ? 31u : 15u;
+    if (props) TRY(run_cal_nu_rho(c));
+    TRY(run_kappa(c));
+    TRY(run_advect(c, true));
+    TRY(run_set_bc(c, mask));
+    TRY(run_rhs(c, true));
+    for (int s = 0; s < c->P.n_jacobi; ++s) TRY(run_jacobi_sweep(c, 0));
+    TRY(run_project(c, true));
+    TRY(run_set_bc(c, mask));
+    if (istep % 2 == 0) { TRY(run_fct_y(c, false)); TRY(run_fct_x(c, true)); }
+    else { TRY(run_fct_x(c, false)); TRY(run_fct_y(c, true)); }
+    TRY(run_set_bc(c, mask));
+    return VOF_OK;
+}
+
+extern "C" int vof2d_step(VofCtx* c, int istep, unsigned flags) {
+    CHECK_CTX(c);
+    CU(cudaSetDevice(c->device));
+    return step_impl(c, istep, flags);
+}
+
+extern "C" int vof2d_run(VofCtx* c, int istep0, int nsteps, unsigned flags) {
+    CHECK_CTX(c);
+    if (nsteps < 0) return fail(VOF_EINVAL, "nsteps must be >= 0");
+    CU(cudaSetDevice(c->device));
+    int istep = istep0;
+    int left = nsteps;
+    const int par = istep0 & 1, fk = (int)(flags & 3u);
+    if (left >= 4) {
+        // capture two consecutive steps (the FCT sweep order alternates with istep parity; after two
+        // steps every ping-pong buffer is back where it started, so the graph can be replayed)
+        if (!c->graph[par][fk]) {
+            const int F0 = c->F_cur, p0 = c->p_cur;
+            cudaGraph_t gr = nullptr;
+            CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = step_impl(c, istep, flags);
+            if (rc == VOF_OK) rc = step_impl(c, istep + 1, flags);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &gr);
+            c->F_cur = F0; c->p_cur = p0;   // capture did not execute anything
+            if (rc != VOF_OK) { if (gr) cudaGraphDestroy(gr); return rc; }
+            if (e != cudaSuccess) return fail((int)e, "stream capture failed: %s", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&c->graph[par][fk], gr, 0);
+            cudaGraphDestroy(gr);
+            if (e != cudaSuccess) { c->graph[par][fk] = nullptr; return fail((int)e, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+        }
+        while (left >= 2) {
+            CU(cudaGraphLaunch(c->graph[par][fk], c->stream));
+            left -= 2; istep += 2;
+        }
+        c->rhs_valid = !(flags & VOF_STEP_NO_FUSION);
+    }
+    for (; left > 0; --left, ++istep) TRY(step_impl(c, istep, flags));
+    return VOF_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// field access
+// ------------------------------------------------------------------------------------
+static float* field_dev(VofCtx* c, int field) {
+    switch (field) {
+        case VOF_F: return c->F();
+        case VOF_U: return c->buf[BUF_U];
+        case VOF_V: return c->buf[BUF_V];
+        case VOF_P: return c->p();
+        case VOF_RHO: return c->buf[BUF_RHO];
+        case VOF_NU: return c->buf[BUF_NU];
+        case VOF_KAPPA: return c->buf[BUF_KAPPA];
+        case VOF_USTAR: return c->buf[BUF_US];
+        case VOF_VSTAR: return c->buf[BUF_VS];
+    }
+    return nullptr;
+}
+
+extern "C" int vof2d_field_ptr(VofCtx* c, int field, float** dev, int64_t* pitch_elems, int64_t* rows) {
+    CHECK_CTX(c);
+    float* d = field_dev(c, field);
+    if (!d) return fail(VOF_EINVAL, "unknown 2-D field id %d", field);
+    if (dev) *dev = d;
+    if (pitch_elems) *pitch_elems = c->g.pitch;
+    if (rows) *rows = c->g.nrows;
+    return VOF_OK;
+}
+
+extern "C" int vof2d_field_get(VofCtx* c, int field, float* host_dst) {
+    CHECK_CTX(c);
+    float* d = field_dev(c, field);
+    if (!d || !host_dst) return fail(VOF_EINVAL, "bad field id %d or null destination", field);
+    CU(cudaSetDevice(c->device));
+    const size_t w = (size_t)(c->g.ny + 2) * sizeof(float);
+    CU(cudaMemcpy2DAsync(host_dst, w, d, (size_t)c->g.pitch * sizeof(float), w, c->g.nrows, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VOF_OK;
+}
+
+static int field_set_async(VofCtx* c, int field, const float* host_src) {
+    float* d = field_dev(c, field);
+    if (!d || !host_src) return fail(VOF_EINVAL, "bad field id %d or null source", field);
+    const size_t w = (size_t)(c->g.ny + 2) * sizeof(float);
+    CU(cudaMemcpy2DAsync(d, (size_t)c->g.pitch * sizeof(float), host_src, w, w, c->g.nrows, cudaMemcpyHostToDevice, c->stream));
+    return VOF_OK;
+}
+
+extern "C" int vof2d_field_set(VofCtx* c, int field, const float* host_src) {
+    CHECK_CTX(c);
+    CU(cudaSetDevice(c->device));
+    TRY(field_set_async(c, field, host_src));
+    CU(cudaStreamSynchronize(c->stream));
+    return VOF_OK;
+}
+
+extern "C" int vof2d_field_fill(VofCtx* c, int field, float value) {
+    CHECK_CTX(c);
+    float* d = field_dev(c, field);
+    if (!d) return fail(VOF_EINVAL, "unknown 2-D field id %d", field);
+    CU(cudaSetDevice(c->device));
+    std::vector<float> row((size_t)c->g.ny + 2, value);
+    std::vector<float> all((size_t)c->g.nrows * (c->g.ny + 2));
+    for (int i = 0; i < c->g.nrows; ++i) memcpy(&all[(size_t)i * (c->g.ny + 2)], row.data(), row.size() * sizeof(float));
+    return vof2d_field_set(c, field, all.data());
+}
+
+extern "C" int vof2d_step_host(VofCtx* c, int istep, unsigned flags, const float* u_in, const float* v_in,
+                               const float* p_in, const float* F_in, float* u_out, float* v_out, float* p_out,
+                               float* F_out) {
+    CHECK_CTX(c);
+    CU(cudaSetDevice(c->device));
+    if (F_in) TRY(field_set_async(c, VOF_F, F_in));
+    if (u_in) TRY(field_set_async(c, VOF_U, u_in));
+    if (v_in) TRY(field_set_async(c, VOF_V, v_in));
+    if (p_in) TRY(field_set_async(c, VOF_P, p_in));
+    TRY(step_impl(c, istep, flags));
+    const size_t w = (size_t)(c->g.ny + 2) * sizeof(float), dp = (size_t)c->g.pitch * sizeof(float);
+    const int ids[4] = {VOF_U, VOF_V, VOF_P, VOF_F};
+    float* outs[4] = {u_out, v_out, p_out, F_out};
+    for (int k = 0; k < 4; ++k)
+        if (outs[k]) CU(cudaMemcpy2DAsync(outs[k], w, field_dev(c, ids[k]), dp, w, c->g.nrows, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return VOF_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// diagnostics
+// ------------------------------------------------------------------------------------
+extern "C" int vof2d_diagnostics(VofCtx* c, double* mass, float* max_cfl, float* residual, int64_t* courant_count) {
+    CHECK_CTX(c);
+    CU(cudaSetDevice(c->device));
+    const int do_resid = residual != nullptr;
+    if (do_resid && !c->rhs_valid) TRY(run_rhs(c, false));   // sequence mode: rho array holds the step's densities
+    // mass / cfl / residual words are reset; courant_count is kept (written by the last projection)
+    CU(cudaMemsetAsync(c->diag, 0, offsetof(Diag, courant_count), c->stream));
+    const int a = std::max(c->lo - c->g.gi0, 0), b = c->hi - c->g.gi0;   // owned rows only
+    dim3 grid(std::min(cdiv(c->g.ny, 256), 64), std::min(b - a + 1, 256));
+    k_diag<<<grid, 256, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_U], c->buf[BUF_V], c->p(), c->buf[BUF_RHS], c->diag, a, b, do_resid);
+    TRY(launch_ok("k_diag"));
+    Diag h;
+    CU(cudaMemcpyAsync(&h, c->diag, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (mass) *mass = h.mass;
+    if (max_cfl) memcpy(max_cfl, &h.max_cfl_bits, sizeof(float));
+    if (residual) memcpy(residual, &h.resid_bits, sizeof(float));
+    if (courant_count) *courant_count = (int64_t)h.courant_count;
+    return VOF_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// slabs: halo rows are contiguous (rows * pitch floats, pad columns included)
+// ------------------------------------------------------------------------------------
+extern "C" int vof2d_halo_rows(const VofCtx* c, int* rows_per_side, int64_t* floats_per_field_side) {
+    CHECK_CTX(c);
+    if (rows_per_side) *rows_per_side = c->H;
+    if (floats_per_field_side) *floats_per_field_side = (int64_t)c->H * c->g.pitch;
+    return VOF_OK;
+}
+
+extern "C" int vof2d_halo_ptr(VofCtx* c, int field, int side, int send, float** dev, int64_t* count) {
+    CHECK_CTX(c);
+    float* d = field_dev(c, field);
+    if (!d || (side != 0 && side != 1)) return fail(VOF_EINVAL, "bad field id %d or side %d", field, side);
+    if ((side == 0 && c->has_lo) || (side == 1 && c->has_hi))
+        return fail(VOF_ESTATE, "side %d of this context is a physical wall, not a slab interface", side);
+    const int H = c->H, n = c->g.nrows;
+    int row;
+    if (side == 0) row = send ? H : 0;                 // lower: send owned rows [H, 2H), receive into [0, H)
+    else row = send ? n - 2 * H : n - H;               // upper: send [n-2H, n-H), receive into [n-H, n)
+    if (dev) *dev = d + (size_t)row * c->g.pitch - kColOff;   // whole pitched rows, from the row start
+    if (count) *count = (int64_t)H * c->g.pitch;
+    return VOF_OK;
+}
+
+extern "C" int vof2d_halo_push(VofCtx* c, int field, int side, float* peer_halo_dst) {
+    CHECK_CTX(c);
+    float* src; int64_t n;
+    TRY(vof2d_halo_ptr(c, field, side, 1, &src, &n));
+    if (!peer_halo_dst) return fail(VOF_EINVAL, "null peer destination");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(peer_halo_dst, src, (size_t)n * sizeof(float), cudaMemcpyDefault, c->stream));
+    return VOF_OK;
+}

@@ -1,0 +1,80 @@
+// Shared definitions for the libvof CUDA translation units (sm_100a only).
+//
+// Arithmetic contract: every kernel evaluates the reference's expressions
+// (/root/reference/2dvof.py) in IEEE fp32, left to right, with NO FMA contraction
+// (this directory is compiled with -fmad=false) and correctly rounded / and sqrt
+// (-prec-div=true -prec-sqrt=true, the nvcc defaults).  Where an FMA is wanted for
+// speed AND proven value-identical it is written explicitly with __fmaf_rn.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vof.h"
+
+namespace vof {
+
+// Column offset of logical j = 0 inside a pitched row: logical j = 1 (first interior
+// column) sits on a 128-byte boundary so interior float4 / warp accesses are aligned.
+constexpr int kColOff = 31;
+constexpr int kPitchAlign = 32;   // floats
+
+// fp32 constants exactly as the reference's kernels see them (double-folded Python
+// scalars rounded once).
+struct Consts {
+    float dt, dx, dy, dxi, dyi, dxi2, dyi2, dxdy, dtdy, dtdx;
+    float m1_2dx, m1_2dy;    // -1/(2*dx), -1/(2*dy)          2dvof.py:287-294
+    float i_dx_2, i_dy_2;    // 1/dx/2, 1/dy/2                2dvof.py:308-309
+    float neg_sigma;         // -sigma[None]                  2dvof.py:213
+    float rho_l, rho_g, nu_l, nu_g, gx, gy;
+    float cflx, cfly;        // 0.25*dx, 0.25*dy              2dvof.py:274, 279
+};
+
+// Geometry of one context's local arrays.  Local row l holds global row gi0 + l.
+struct Grid {
+    int nx, ny;      // global interior size
+    int gi0;         // global i of local row 0 (0 for a full-domain context)
+    int nrows;       // local rows allocated
+    int pitch;       // floats per row
+};
+
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---- order-exact scalar helpers -------------------------------------------------
+// 2dvof.py:192-195  var(a,b,c) = a+b+c - max(a,b,c) - min(a,b,c)
+__device__ __forceinline__ float var3(float a, float b, float c) {
+    float s = (a + b) + c;
+    float mx = fmaxf(fmaxf(a, b), c);
+    float mn = fminf(fminf(a, b), c);
+    return (s - mx) - mn;
+}
+// var(0, 1, x) and var(x, 0, 1) are the same function of x: (1+x) - max(1,x) - min(0,x)
+__device__ __forceinline__ float var01(float x) {
+    return ((1.0f + x) - fmaxf(1.0f, x)) - fminf(0.0f, x);
+}
+// 2dvof.py:201-203
+__device__ __forceinline__ float rho_of(float F, const Consts& c) {
+    float f = var01(F);
+    return c.rho_g * (1.0f - f) + c.rho_l * f;
+}
+__device__ __forceinline__ float nu_of(float F, const Consts& c) {
+    float f = var01(F);
+    return c.nu_l * f + c.nu_g * (1.0f - f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace vof
