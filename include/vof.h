@@ -132,6 +132,16 @@ int vof2d_field_fill(VofCtx* c, int field, float value);
  * with u*dt > 0.25*dx (the reference's print condition).  Any pointer may be NULL.  Synchronous. */
 int vof2d_diagnostics(VofCtx* c, double* mass, float* max_cfl, float* residual, int64_t* courant_count);
 
+/* ---- measurement support (new): every kernel launch is counted; with profiling on, each launch
+ * group is bracketed by CUDA events recorded on the context's stream (not usable under graph replay). */
+enum {
+    VOF_K_PROPS = 0, VOF_K_KAPPA, VOF_K_ADVECT, VOF_K_BC, VOF_K_RHS, VOF_K_JACOBI, VOF_K_PROJECT,
+    VOF_K_FCT_X, VOF_K_FCT_Y, VOF_K_POST, VOF_K_HALO, VOF_K_COUNT
+};
+int64_t vof2d_launch_count(const VofCtx* c);
+int vof2d_profile(VofCtx* c, int enable);                 /* enable/disable; always resets the spans */
+int vof2d_profile_read(VofCtx* c, int kind, double* ms_total, int64_t* spans);  /* synchronous */
+
 /* ---- slabs (new): halo rows are contiguous runs of `pitch` floats.  Pack/unpack the rows the
  * neighbours need; the transport (NVLink P2P / NCCL) is the caller's.  side: 0 = lower i, 1 = upper. */
 int vof2d_halo_rows(const VofCtx* c, int* rows_per_side, int64_t* floats_per_field_side);

@@ -57,6 +57,8 @@ extern "C" void vof_default_params(VofParams* p) {
 // ------------------------------------------------------------------------------------
 enum { BUF_F0 = 0, BUF_F1, BUF_U, BUF_V, BUF_P0, BUF_P1, BUF_US, BUF_VS, BUF_RHS, BUF_KAPPA, BUF_RHO, BUF_NU, BUF_COUNT };
 
+struct ProfSpan { int kind; cudaEvent_t a, b; };
+
 struct VofCtx {
     VofParams P;
     Grid g;
@@ -80,6 +82,12 @@ struct VofCtx {
     int in_a, in_b;            // rows whose global index is in [1, nx]
     // CUDA graphs of two consecutive steps, keyed by parity of the first istep and flags
     cudaGraphExec_t graph[2][4];
+    long long graph_launches[2][4];
+    // launch accounting + optional per-kernel-kind CUDA-event timing (vof2d_profile)
+    long long launches;
+    bool profiling;
+    std::vector<cudaEvent_t>* ev_pool;        // recycled events
+    std::vector<ProfSpan>* spans;             // (kind, start, stop) recorded on c->stream
     float* F() { return buf[F_cur ? BUF_F1 : BUF_F0]; }
     float* F_alt() { return buf[F_cur ? BUF_F0 : BUF_F1]; }
     float* p() { return buf[p_cur ? BUF_P1 : BUF_P0]; }
@@ -217,6 +225,8 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     CU(cudaMemcpy(c->ys, y.data(), y.size() * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
+    c->ev_pool = new std::vector<cudaEvent_t>();
+    c->spans = new std::vector<ProfSpan>();
     *out = c;
     return VOF_OK;
 }
@@ -234,6 +244,8 @@ extern "C" int vof2d_destroy(VofCtx* c) {
     for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 4; ++b)
             if (c->graph[a][b]) cudaGraphExecDestroy(c->graph[a][b]);
+    if (c->spans) { for (auto& sp : *c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); } delete c->spans; }
+    if (c->ev_pool) { for (auto e : *c->ev_pool) cudaEventDestroy(e); delete c->ev_pool; }
     if (c->own_arena && c->arena) cudaFree(c->arena);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);   // a caller-provided stream is left alone
     delete c;
@@ -275,12 +287,28 @@ static int launch_ok(const char* what) {
     if (e != cudaSuccess) return fail((int)e, "launch of %s failed: %s", what, cudaGetErrorString(e));
     return VOF_OK;
 }
+// RAII span: counts the launch and, when profiling, brackets it with events on the ctx stream
+struct Span {
+    VofCtx* c; int kind; cudaEvent_t b;
+    Span(VofCtx* c_, int kind_, int nlaunch = 1) : c(c_), kind(kind_), b(nullptr) {
+        c->launches += nlaunch;
+        if (!c->profiling) return;
+        cudaEvent_t a;
+        auto get = [&]() { cudaEvent_t e; if (!c->ev_pool->empty()) { e = c->ev_pool->back(); c->ev_pool->pop_back(); } else cudaEventCreate(&e); return e; };
+        a = get(); b = get();
+        cudaEventRecord(a, c->stream);
+        c->spans->push_back({kind, a, b});
+    }
+    ~Span() { if (b) cudaEventRecord(b, c->stream); }
+};
+
 constexpr int kRowsPerBlock = 32;   // rows marched by one block of the streaming kernels
 constexpr int kFctRows = 64;        // x-sweep chunk (6 warm-up rows are re-read per chunk)
 
 static unsigned bc_mask_all = 31u;
 
 static int run_set_bc(VofCtx* c, unsigned mask) {
+    Span span_(c, VOF_K_BC);
     const int nA = c->all_b - c->all_a + 1;
     const int nB = c->g.ny + 2;
     const int n = nA + (c->has_lo ? nB : 0) + (c->has_hi ? nB : 0);
@@ -290,6 +318,7 @@ static int run_set_bc(VofCtx* c, unsigned mask) {
 }
 
 static int run_cal_nu_rho(VofCtx* c) {
+    Span span_(c, VOF_K_PROPS);
     const int rows = c->all_b - c->all_a + 1;
     dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, kRowsPerBlock));
     k_cal_nu_rho<<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_RHO], c->buf[BUF_NU], c->all_a, c->all_b, kRowsPerBlock);
@@ -297,6 +326,7 @@ static int run_cal_nu_rho(VofCtx* c) {
 }
 
 static int run_kappa(VofCtx* c) {
+    Span span_(c, VOF_K_KAPPA);
     constexpr int TI = 16, TJ = 64;
     const int rows = c->in_b - c->in_a + 1;
     dim3 grid(cdiv(c->g.ny, TJ), cdiv(rows, TI));
@@ -305,6 +335,7 @@ static int run_kappa(VofCtx* c) {
 }
 
 static int run_advect(VofCtx* c, bool inline_props) {
+    Span span_(c, VOF_K_ADVECT);
     const int a = std::max(c->in_a, 1), b = std::min(c->in_b, c->g.nrows - 2);
     const int rows = b - a + 1;
     dim3 grid(cdiv(c->g.ny, kBlockJ), cdiv(rows, kRowsPerBlock));
@@ -318,6 +349,7 @@ static int run_advect(VofCtx* c, bool inline_props) {
 }
 
 static int run_rhs(VofCtx* c, bool inline_props) {
+    Span span_(c, VOF_K_RHS);
     const int a = c->in_a, b = std::min(c->in_b, c->g.nrows - 2);
     const int rows = b - a + 1;
     dim3 grid(cdiv(c->g.ny, kBlockJ), cdiv(rows, kRowsPerBlock));
@@ -331,6 +363,7 @@ static int run_rhs(VofCtx* c, bool inline_props) {
 
 // one sweep, rhs_mode as in k_jacobi
 static int run_jacobi_sweep(VofCtx* c, int rhs_mode) {
+    Span span_(c, VOF_K_JACOBI);
     const int rows = c->all_b - c->all_a + 1;
     dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, kRowsPerBlock));
     const float* rhoF = rhs_mode == 2 ? c->F() : c->buf[BUF_RHO];
@@ -344,19 +377,21 @@ static int run_jacobi_sweep(VofCtx* c, int rhs_mode) {
 }
 
 static int run_project(VofCtx* c, bool inline_props) {
+    Span span_(c, VOF_K_PROJECT);
     const int a = std::max(c->in_a, 1), b = c->in_b;
     const int rows = b - a + 1;
     dim3 grid(cdiv(c->g.ny, kBlockJ), cdiv(rows, kRowsPerBlock));
     unsigned long long* cc = &c->diag->courant_count;
     CU(cudaMemsetAsync(cc, 0, sizeof(*cc), c->stream));
     if (inline_props)
-        k_project<true><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->p(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_U], c->buf[BUF_V], cc, a, b, kRowsPerBlock);
+        k_project<true><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->p(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_U], c->buf[BUF_V], cc, a, b, kRowsPerBlock, c->lo - c->g.gi0, c->hi - c->g.gi0);
     else
-        k_project<false><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->buf[BUF_RHO], c->p(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_U], c->buf[BUF_V], cc, a, b, kRowsPerBlock);
+        k_project<false><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->buf[BUF_RHO], c->p(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_U], c->buf[BUF_V], cc, a, b, kRowsPerBlock, c->lo - c->g.gi0, c->hi - c->g.gi0);
     return launch_ok("k_project");
 }
 
 static int run_fct_x(VofCtx* c, bool post) {
+    Span span_(c, VOF_K_FCT_X);
     const int rows = c->in_b - c->in_a + 1;
     dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, kFctRows));
     if (post) k_fct_x<true><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, kFctRows);
@@ -366,6 +401,7 @@ static int run_fct_x(VofCtx* c, bool post) {
 }
 
 static int run_fct_y(VofCtx* c, bool post) {
+    Span span_(c, VOF_K_FCT_Y);
     constexpr int TR = 4, TJ = 256;
     const int rows = c->all_b - c->all_a + 1;
     dim3 grid(cdiv(c->g.ny, TJ), cdiv(rows, TR));
@@ -376,6 +412,7 @@ static int run_fct_y(VofCtx* c, bool post) {
 }
 
 static int run_post(VofCtx* c) {
+    Span span_(c, VOF_K_POST);
     const int rows = c->all_b - c->all_a + 1;
     dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, kRowsPerBlock));
     k_post_process_f<<<grid, kBlockJ, 0, c->stream>>>(c->g, c->F(), c->all_a, c->all_b, kRowsPerBlock);
@@ -469,17 +506,20 @@ extern "C" int vof2d_run(VofCtx* c, int istep0, int nsteps, unsigned flags) {
     int istep = istep0;
     int left = nsteps;
     const int par = istep0 & 1, fk = (int)(flags & 3u);
-    if (left >= 4) {
+    if (left >= 4 && !c->profiling) {
         // capture two consecutive steps (the FCT sweep order alternates with istep parity; after two
         // steps every ping-pong buffer is back where it started, so the graph can be replayed)
         if (!c->graph[par][fk]) {
             const int F0 = c->F_cur, p0 = c->p_cur;
+            const long long l0 = c->launches;
             cudaGraph_t gr = nullptr;
             CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
             int rc = step_impl(c, istep, flags);
             if (rc == VOF_OK) rc = step_impl(c, istep + 1, flags);
             cudaError_t e = cudaStreamEndCapture(c->stream, &gr);
             c->F_cur = F0; c->p_cur = p0;   // capture did not execute anything
+            c->graph_launches[par][fk] = c->launches - l0;
+            c->launches = l0;
             if (rc != VOF_OK) { if (gr) cudaGraphDestroy(gr); return rc; }
             if (e != cudaSuccess) return fail((int)e, "stream capture failed: %s", cudaGetErrorString(e));
             e = cudaGraphInstantiate(&c->graph[par][fk], gr, 0);
@@ -488,6 +528,7 @@ extern "C" int vof2d_run(VofCtx* c, int istep0, int nsteps, unsigned flags) {
         }
         while (left >= 2) {
             CU(cudaGraphLaunch(c->graph[par][fk], c->stream));
+            c->launches += c->graph_launches[par][fk];
             left -= 2; istep += 2;
         }
         c->rhs_valid = !(flags & VOF_STEP_NO_FUSION);
@@ -637,5 +678,37 @@ extern "C" int vof2d_halo_push(VofCtx* c, int field, int side, float* peer_halo_
     if (!peer_halo_dst) return fail(VOF_EINVAL, "null peer destination");
     CU(cudaSetDevice(c->device));
     CU(cudaMemcpyAsync(peer_halo_dst, src, (size_t)n * sizeof(float), cudaMemcpyDefault, c->stream));
+    return VOF_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// launch accounting / per-kernel timing (measurement support; not on the hot path)
+// ------------------------------------------------------------------------------------
+extern "C" int64_t vof2d_launch_count(const VofCtx* c) { return c ? (int64_t)c->launches : -1; }
+
+extern "C" int vof2d_profile(VofCtx* c, int enable) {
+    CHECK_CTX(c);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto& sp : *c->spans) { c->ev_pool->push_back(sp.a); c->ev_pool->push_back(sp.b); }
+    c->spans->clear();
+    c->profiling = enable != 0;
+    return VOF_OK;
+}
+
+extern "C" int vof2d_profile_read(VofCtx* c, int kind, double* ms_total, int64_t* spans) {
+    CHECK_CTX(c);
+    if (kind < 0 || kind >= VOF_K_COUNT) return fail(VOF_EINVAL, "bad kernel kind %d", kind);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    double tot = 0.0; int64_t n = 0;
+    for (auto& sp : *c->spans) {
+        if (sp.kind != kind) continue;
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        tot += ms; ++n;
+    }
+    if (ms_total) *ms_total = tot;
+    if (spans) *spans = n;
     return VOF_OK;
 }

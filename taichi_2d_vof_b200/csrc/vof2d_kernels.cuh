@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kBlockJ)
 k_project(Grid g, Consts c, const float* __restrict__ rhoF, const float* __restrict__ p,
           const float* __restrict__ us, const float* __restrict__ vs, float* __restrict__ u,
           float* __restrict__ v, unsigned long long* __restrict__ courant_count, int r0, int r1,
-          int rows_per_block) {
+          int rows_per_block, int own_a, int own_b) {
     const int j = 1 + blockIdx.x * kBlockJ + threadIdx.x;
     if (j > g.ny) return;
     const int ia = r0 + blockIdx.y * rows_per_block;
@@ -332,14 +332,14 @@ k_project(Grid g, Consts c, const float* __restrict__ rhoF, const float* __restr
             const float r = (rho_c + rho_m) * 0.5f;
             const float un = us[o] - ((c.dt / r) * (p_c - p_m)) * c.dxi;
             u[o] = un;
-            flags += (un * c.dt > c.cflx);
+            flags += (un * c.dt > c.cflx) && i >= own_a && i <= own_b;
         }
         if (j >= 2 && gi >= 1 && gi <= g.nx) {
             const float rho_jm = INLINE_PROPS ? rho_of(rhoF[o - 1], c) : rhoF[o - 1];
             const float r = (rho_c + rho_jm) * 0.5f;
             const float vn = vs[o] - ((c.dt / r) * (p_c - p[o - 1])) * c.dyi;
             v[o] = vn;
-            flags += (vn * c.dt > c.cfly);
+            flags += (vn * c.dt > c.cfly) && i >= own_a && i <= own_b;
         }
         p_m = p_c; rho_m = rho_c;
     }

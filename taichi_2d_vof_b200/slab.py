@@ -1,0 +1,125 @@
+"""Row-slab decomposition over the GPUs of one NVSwitch box (new capability; the reference is
+single-address-space).
+
+Design: communication-avoiding deep halos.  The whole timestep has a dependency radius of
+``n_jacobi + 3`` rows along i (kappa 2, advect +1, ten Jacobi sweeps +10 ... the x-FCT needs u at
+i+3 -- see DESIGN.md), so each rank keeps H >= n_jacobi + 3 ghost rows per side, recomputes
+the few halo rows redundantly, and exchanges u, v, p, F ONCE per step (4 fields x H contiguous
+pitched rows per neighbour) instead of once per sweep.  Physical-wall logic applies only on the
+first / last rank; interior ranks see their neighbours' rows as ordinary cells.
+
+Transport: ``torch.distributed`` P2P (NCCL over NVLink on the GPU box; gloo on CPU for the
+host-logic tests).  ``partition`` / ``exchange`` are pure host logic and device-agnostic.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+HALO_FIELDS = ("F", "u", "v", "p")
+
+
+def partition(nx: int, nranks: int) -> List[Tuple[int, int]]:
+    """Owned global interior rows [lo, hi] (inclusive, 1-based) of every rank; remainders go to
+    the low ranks so slab heights differ by at most one."""
+    if nranks < 1 or nx < nranks:
+        raise ValueError(f"cannot split {nx} rows over {nranks} ranks")
+    base, rem = divmod(nx, nranks)
+    out, lo = [], 1
+    for r in range(nranks):
+        n = base + (1 if r < rem else 0)
+        out.append((lo, lo + n - 1))
+        lo += n
+    return out
+
+
+def required_halo(n_jacobi: int) -> int:
+    """Dependency radius of one step along i (matches VOF_SLAB_MIN_HALO for n_jacobi = 10)."""
+    return n_jacobi + 3
+
+
+def halo_row_blocks(nrows: int, halo: int):
+    """Local row ranges [a, b) of the four halo blocks of a slab with `nrows` local rows:
+    (send_lo, recv_lo, send_hi, recv_hi).  Mirrors vof2d_halo_ptr."""
+    H = halo
+    return ((H, 2 * H), (0, H), (nrows - 2 * H, nrows - H), (nrows - H, nrows))
+
+
+def exchange(dist, rank: int, nranks: int, send_lo: Sequence, recv_lo: Sequence, send_hi: Sequence,
+             recv_hi: Sequence):
+    """One halo exchange: every tensor in send_lo goes to rank-1's recv_hi, send_hi to rank+1's
+    recv_lo.  Tensors are contiguous 1-D views; lists are per field in the same order on all ranks."""
+    ops = []
+    if rank > 0:
+        for t in send_lo:
+            ops.append(dist.P2POp(dist.isend, t, rank - 1))
+        for t in recv_lo:
+            ops.append(dist.P2POp(dist.irecv, t, rank - 1))
+    if rank < nranks - 1:
+        for t in send_hi:
+            ops.append(dist.P2POp(dist.isend, t, rank + 1))
+        for t in recv_hi:
+            ops.append(dist.P2POp(dist.irecv, t, rank + 1))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+class SlabSolver2D:
+    """One rank's slab of a global (nx, ny) domain.  ``step()`` = halo exchange + the fused step."""
+
+    def __init__(self, global_params_fn, nx: int, rank: int, nranks: int, dist=None, halo: int | None = None,
+                 n_jacobi: int = 10, device: int = -1):
+        import torch
+        from .solver2d import VofSolver2D
+        self.rank, self.nranks, self.dist = rank, nranks, dist
+        self.parts = partition(nx, nranks)
+        self.lo, self.hi = self.parts[rank]
+        H = halo if halo is not None else max(required_halo(n_jacobi), 16)
+        if nranks == 1:
+            params = global_params_fn(slab=None, halo=0, device=device)
+        else:
+            params = global_params_fn(slab=(self.lo, self.hi), halo=H, device=device)
+        self.stream = torch.cuda.Stream(device=device if device >= 0 else None)
+        self.solver = VofSolver2D(params, stream=self.stream)
+        self.halo = self.solver.halo
+        self._views = None
+
+    def _halo_views(self):
+        """torch views of the 4 x 4 halo blocks (whole pitched rows, contiguous)."""
+        import torch
+        s = self.solver
+        views = {}
+        for side, has_nbr in ((0, self.rank > 0), (1, self.rank < self.nranks - 1)):
+            for send in (1, 0):
+                lst = []
+                if has_nbr:
+                    for name in HALO_FIELDS:
+                        addr, n = s.halo_ptr(name, side, send)
+
+                        class _Blob:
+                            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (addr, False),
+                                                        "version": 3, "strides": None}
+                        lst.append(torch.as_tensor(_Blob(), device=f"cuda:{s.device}"))
+                views[(side, send)] = lst
+        return views
+
+    def exchange_halos(self):
+        if self.nranks == 1:
+            return
+        import torch
+        v = self._halo_views()   # re-queried every step: F and p ping-pong between two buffers
+        with torch.cuda.stream(self.stream):
+            exchange(self.dist, self.rank, self.nranks, v[(0, 1)], v[(0, 0)], v[(1, 1)], v[(1, 0)])
+
+    def set_init_F(self, ic):
+        self.solver.set_init_F(ic)
+
+    def step(self):
+        self.exchange_halos()
+        self.solver.step()
+
+    def owned(self, name):
+        """This rank's owned interior rows of a field, as numpy (rows lo..hi, all columns)."""
+        a = getattr(self.solver, name).to_numpy()
+        H = self.solver.halo
+        return a[H:a.shape[0] - H]

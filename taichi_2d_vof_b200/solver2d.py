@@ -49,8 +49,11 @@ class Field:
     def shape(self):
         return (self._s.nrows, self._s.ny + 2)
 
-    def to_numpy(self) -> np.ndarray:
-        out = np.empty(self.shape, dtype=np.float32)
+    def to_numpy(self, out=None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.shape, dtype=np.float32)
+        elif out.shape != self.shape or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError(f"field {self.name}: out must be C-contiguous float32 {self.shape}")
         check(self._s._L.vof2d_field_get(self._s._h, self.fid, out.ctypes.data_as(C.c_void_p)))
         return out
 
@@ -233,6 +236,23 @@ class VofSolver2D:
 
     def state(self):
         return {k: getattr(self, k).to_numpy() for k in self.FIELDS}
+
+    # ---- measurement support
+    def launch_count(self):
+        return int(self._L.vof2d_launch_count(self._h))
+
+    def profile(self, enable=True):
+        check(self._L.vof2d_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """{kind: (total ms, launches)} of the spans recorded since profile(True)."""
+        out = {}
+        for k, name in enumerate(_lib.KERNEL_KINDS):
+            ms, n = C.c_double(), C.c_int64()
+            check(self._L.vof2d_profile_read(self._h, k, C.byref(ms), C.byref(n)))
+            if n.value:
+                out[name] = (ms.value, n.value)
+        return out
 
     # ---- slabs
     def halo_ptr(self, name, side, send):
