@@ -1,0 +1,143 @@
+"""CPU tests of the oracle: the two independent restatements (NumPy slices / C loops) must agree
+bit for bit, reproduce the committed golden vectors, and satisfy the known answers and invariants
+that follow from the reference source."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle.c_oracle import Vof2DCOracle
+from oracle.vof2d_oracle import Vof2DOracle, Vof2DParams, rel_linf
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIELDS = ("F", "u", "v", "p", "rho", "nu", "kappa", "u_star", "v_star")
+
+
+@pytest.mark.parametrize("ic", [1, 2, 3])
+@pytest.mark.parametrize("shape", [(40, 40), (33, 57)])
+def test_numpy_and_c_oracles_identical(ic, shape):
+    nx, ny = shape
+    P = Vof2DParams(nx=nx, ny=ny, Lx=0.1 * nx / 200, Ly=0.1 * ny / 200)
+    a, b = Vof2DOracle(P), Vof2DCOracle(P)
+    a.set_init_F(ic); b.set_init_F(ic)
+    for _ in range(12):
+        a.step(); b.step()
+    for k in FIELDS:
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert a.courant_flags == b.courant_flags
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "vof2d_ic*_*.npz"))))
+def test_c_oracle_reproduces_golden(path):
+    g = np.load(path)
+    nx, ny, Lx, Ly = int(g["params"][0]), int(g["params"][1]), float(g["params"][2]), float(g["params"][3])
+    ic = int(os.path.basename(path)[8])
+    o = Vof2DCOracle(Vof2DParams(nx=nx, ny=ny, Lx=Lx, Ly=Ly))
+    assert abs(o.P.dx - g["params"][4]) == 0 and abs(o.P.dy - g["params"][5]) == 0
+    o.set_init_F(ic)
+    assert np.array_equal(o.F, g["F_init"])
+    for ck in (1, 10, 100):
+        o.run(ck - o.istep)
+        for k in ("u", "v", "p", "F", "kappa"):
+            assert np.array_equal(getattr(o, k), g[f"{k}_{ck}"]), f"{k} after {ck} steps"
+        assert abs(o.mass() - float(g[f"mass_{ck}"])) <= 1e-9 * float(g[f"mass_{ck}"])
+
+
+def test_numpy_oracle_reproduces_golden_small():
+    g = np.load(os.path.join(GOLD, "vof2d_ic3_64x96.npz"))
+    o = Vof2DOracle(Vof2DParams(nx=64, ny=96, Lx=0.032, Ly=0.048))
+    o.set_init_F(3)
+    o.run(10)
+    for k in ("u", "v", "p", "F", "kappa"):
+        assert np.array_equal(getattr(o, k), g[f"{k}_10"]), k
+
+
+def test_default_constants_match_reference_source():
+    """2dvof.py:19-50: dx is a difference of two fp32 node coordinates, not Lx/nx."""
+    P = Vof2DParams()
+    assert (P.nx, P.ny, P.dt, P.n_jacobi) == (200, 200, 4e-6, 10)
+    assert P.dx == float(np.float32(0.001)) - float(np.float32(0.0005))
+    assert abs(P.dx - 5.000000237e-4) < 1e-13 and P.dx != 5e-4
+    o = Vof2DOracle(P)
+    assert o.c_dxi2 == np.float32((1 / P.dx) ** 2)
+
+
+def test_var_is_arithmetic_not_a_clamp():
+    """2dvof.py:192-195 quantises to multiples of 2^-23."""
+    o = Vof2DOracle(Vof2DParams(nx=8, ny=8))
+    f = np.float32
+    assert o._var(f(0), f(1), f(0.3)) == f(0.29999995)
+    assert o._var(f(0), f(1), f(3.3e-8)) == f(0)
+    assert o._var(f(0), f(1), f(1.0000001)) == f(0.9999999)
+    assert o._var(f(0), f(1), f(-1e-9)) > 0
+
+
+def test_step1_dam_break_known_answers():
+    """From rest: u* = 0, v* = dt*gy = -2e-5 in the bulk; F is unchanged where u = v = 0."""
+    o = Vof2DOracle(Vof2DParams())
+    o.set_init_F(1)
+    F0 = o.F.copy()
+    o.istep += 1
+    o.cal_nu_rho(); o.get_normal_young(); o.advect_upwind()
+    assert np.all(o.u_star[2:200, 1:201][:, 120:] == 0)                    # gas region far from the interface
+    assert np.all(o.v_star[1:201, 2:201][100:, 120:] == np.float32(4e-6) * np.float32(-5))
+    assert np.all(o.u_star[1, :] == 0) and np.all(o.u_star[201, :] == 0)     # walls never written
+    assert np.all(o.v_star[:, 1] == 0) and np.all(o.v_star[:, 201] == 0)
+    # rho, nu of the two pure phases
+    assert o.rho[10, 10] == np.float32(1000.0) and o.rho[150, 150] == np.float32(50.0)
+    # F only changes next to the interface during the first step
+    o2 = Vof2DOracle(Vof2DParams()); o2.set_init_F(1); o2.step()
+    changed = np.argwhere(o2.F != F0)
+    assert len(changed) < 4 * 200
+
+
+@pytest.mark.parametrize("ic", [1, 2, 3])
+def test_bounds_and_volume(ic):
+    o = Vof2DCOracle(Vof2DParams())
+    o.set_init_F(ic)
+    m0 = o.mass()
+    o.run(100)
+    assert o.F.min() >= 0.0 and o.F.max() <= 1.0
+    # the scheme itself (clamps + 2^-23 quantisation) drifts by a few 1e-6 in 100 steps
+    assert abs(o.mass() - m0) / m0 < 1e-5
+
+
+def test_fct_transposition_symmetry():
+    """fct_x on (F, u) is fct_y on (F^T, v = u^T) when dx == dy -- same arithmetic, transposed."""
+    rng = np.random.default_rng(1)
+    P = Vof2DParams(nx=48, ny=48, Lx=0.024, Ly=0.024)
+    a, b = Vof2DOracle(P), Vof2DOracle(P)
+    F = rng.random(a.F.shape, dtype=np.float32)
+    u = (rng.random(a.F.shape, dtype=np.float32) - 0.5) * 4
+    a.F[...] = F; a.u[...] = u
+    b.F[...] = F.T; b.v[...] = u.T
+    a.fct_x_sweep(); b.fct_y_sweep()
+    assert np.array_equal(a.F, b.F.T)
+
+
+def test_set_bc_corner_order():
+    """Row loop then column loop: corners take the column loop's copy of the row loop's result."""
+    rng = np.random.default_rng(2)
+    o = Vof2DOracle(Vof2DParams(nx=6, ny=7, Lx=0.003, Ly=0.0035))
+    for k in ("u", "v", "F", "p", "rho"):
+        getattr(o, k)[...] = rng.random(o.F.shape, dtype=np.float32)
+    F = o.F.copy()
+    o.set_BC()
+    assert o.F[0, 0] == F[1, 1] and o.F[7, 8] == F[6, 7] and o.F[0, 8] == F[1, 7]
+    assert np.all(o.u[1, :] == 0) and np.all(o.u[7, :] == 0)
+    assert np.all(o.v[:, 1] == 0) and np.all(o.v[:, 8] == 0)
+
+
+def test_roundoff_perturbation_stays_within_north_star_tolerance():
+    """Calibrates the 1e-3 @ 100 steps gate: a 1-ulp perturbation of v after the first step (the size
+    of difference a differently-rounding compiler would introduce) must not grow beyond it in
+    u, v, p, F.  (kappa is NOT stable in this sense: cells with |normal| ~ 1e-8 flip direction.)"""
+    P = Vof2DParams(nx=100, ny=100, Lx=0.05, Ly=0.05)
+    a, b = Vof2DCOracle(P), Vof2DCOracle(P)
+    a.set_init_F(3); b.set_init_F(3)
+    a.step(); b.step()
+    b.v[...] = np.nextafter(b.v, np.float32(np.inf))
+    a.run(99); b.run(99)
+    for k in ("u", "v", "p", "F"):
+        assert rel_linf(getattr(b, k), getattr(a, k)) < 1e-3, k
