@@ -142,6 +142,10 @@ int64_t vof2d_launch_count(const VofCtx* c);
 int vof2d_profile(VofCtx* c, int enable);                 /* enable/disable; always resets the spans */
 int vof2d_profile_read(VofCtx* c, int kind, double* ms_total, int64_t* spans);  /* synchronous */
 
+/* tuning knobs for A/B measurements (defaults = fast paths; results are identical either way) */
+enum { VOF_OPT_JACOBI_TB = 0 /* 1: <= 5 sweeps per HBM pass (default), 0: one launch per sweep */ };
+int vof2d_set_option(VofCtx* c, int option, int value);
+
 /* ---- slabs (new): halo rows are contiguous runs of `pitch` floats.  Pack/unpack the rows the
  * neighbours need; the transport (NVLink P2P / NCCL) is the caller's.  side: 0 = lower i, 1 = upper. */
 int vof2d_halo_rows(const VofCtx* c, int* rows_per_side, int64_t* floats_per_field_side);

@@ -18,6 +18,7 @@ VOF_F, VOF_U, VOF_V, VOF_P, VOF_RHO, VOF_NU, VOF_KAPPA, VOF_USTAR, VOF_VSTAR, VO
 FIELD_IDS = {"F": VOF_F, "u": VOF_U, "v": VOF_V, "p": VOF_P, "rho": VOF_RHO, "nu": VOF_NU,
              "kappa": VOF_KAPPA, "u_star": VOF_USTAR, "v_star": VOF_VSTAR, "w": VOF_W, "w_star": VOF_WSTAR}
 KERNEL_KINDS = ("props", "kappa", "advect", "bc", "rhs", "jacobi", "project", "fct_x", "fct_y", "post", "halo")
+VOF_OPT_JACOBI_TB = 0
 VOF_STEP_MATERIALIZE_PROPS = 1
 VOF_STEP_NO_FUSION = 2
 VOF_SLAB_MIN_HALO = 13
@@ -91,6 +92,7 @@ SIGNATURES = {
     "vof2d_launch_count": (C.c_int64, [_ctx]),
     "vof2d_profile": (C.c_int, [_ctx, C.c_int]),
     "vof2d_profile_read": (C.c_int, [_ctx, C.c_int, _P(C.c_double), _P(C.c_int64)]),
+    "vof2d_set_option": (C.c_int, [_ctx, C.c_int, C.c_int]),
     "vof2d_halo_rows": (C.c_int, [_ctx, _P(C.c_int), _P(C.c_int64)]),
     "vof2d_halo_ptr": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _P(C.c_void_p), _P(C.c_int64)]),
     "vof2d_halo_push": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p]),

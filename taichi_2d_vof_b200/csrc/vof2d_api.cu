@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "vof2d_kernels.cuh"
+#include "vof2d_jacobi_tb.cuh"
 
 using namespace vof;
 
@@ -83,6 +84,10 @@ struct VofCtx {
     // CUDA graphs of two consecutive steps, keyed by parity of the first istep and flags
     cudaGraphExec_t graph[2][4];
     long long graph_launches[2][4];
+    JacTB jac;                 // constants of the temporally blocked Jacobi
+    int jac_resident_warps[6]; // warps of k_jacobi_tb<T> resident on the whole GPU, by T
+    int opt_jacobi_tb;         // 1: temporal blocking (default), 0: one launch per sweep
+    int sm_count;
     // launch accounting + optional per-kernel-kind CUDA-event timing (vof2d_profile)
     long long launches;
     bool profiling;
@@ -198,6 +203,21 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     c->ic2 = ic; c->ic2.cy = 2.0f * ic.r;                 // cy = 2 * r in fp32 (r is a kernel local)
     c->ic3 = ic; c->ic3.cy = (float)P.Ly - 3.0f * ic.r;   // Ly - 3 * r in fp32
 
+    {   // diagonal of the Poisson stencil by wall class, summed in the reference's order (2dvof.py:258-262)
+        JacTB& j = c->jac;
+        j.cx = k.dxi2; j.cy = k.dyi2;
+        for (int ic = 0; ic < 2; ++ic)
+            for (int jc2 = 0; jc2 < 2; ++jc2) {
+                const float ae = j.cx, aw = ic ? 0.0f : j.cx, an = j.cy, as = jc2 ? 0.0f : j.cy;
+                volatile float sum = ae + aw; sum = sum + an; sum = sum + as;
+                j.ap[ic][jc2] = -1.0f * sum;
+            }
+        j.rap[0] = (float)(1.0 / (double)j.ap[0][0]);
+        j.rap[1] = (float)(1.0 / (double)j.ap[0][1]);
+        j.fast_div_ok = 0;
+    }
+    c->opt_jacobi_tb = 1;
+    c->sm_count = prop.multiProcessorCount;
     c->all_a = std::max(0, -g.gi0);
     c->all_b = std::min(g.nrows - 1, P.nx + 1 - g.gi0);
     c->in_a = std::max(0, 1 - g.gi0);
@@ -225,6 +245,17 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     CU(cudaMemcpy(c->ys, y.data(), y.size() * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
+    {   // prove the reciprocal division exact for this diagonal: every fp32 numerator against __fdiv_rn
+        unsigned long long* bad = &c->diag->courant_count;
+        CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
+        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->jac.ap[0][0], c->jac.rap[0], bad);
+        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->jac.ap[0][1], c->jac.rap[1], bad);
+        unsigned long long h = 1;
+        CU(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
+        c->jac.fast_div_ok = (h == 0);
+    }
     c->ev_pool = new std::vector<cudaEvent_t>();
     c->spans = new std::vector<ProfSpan>();
     *out = c;
@@ -287,6 +318,8 @@ static int launch_ok(const char* what) {
     if (e != cudaSuccess) return fail((int)e, "launch of %s failed: %s", what, cudaGetErrorString(e));
     return VOF_OK;
 }
+#define TRY(x) do { int rc_ = (x); if (rc_ != VOF_OK) return rc_; } while (0)
+
 // RAII span: counts the launch and, when profiling, brackets it with events on the ctx stream
 struct Span {
     VofCtx* c; int kind; cudaEvent_t b;
@@ -376,6 +409,67 @@ static int run_jacobi_sweep(VofCtx* c, int rhs_mode) {
     return launch_ok("k_jacobi");
 }
 
+template <int T>
+static int launch_jacobi_tb(VofCtx* c, const float* pin, float* pout) {
+    const int rows = c->in_b - c->in_a + 1;
+    auto kern = c->jac.fast_div_ok ? k_jacobi_tb<T, true> : k_jacobi_tb<T, false>;
+    if (!c->jac_resident_warps[T]) {
+        int nb = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * kJacWarpsPerBlock, 0));
+        c->jac_resident_warps[T] = std::max(1, nb) * kJacWarpsPerBlock * c->sm_count;
+    }
+    JacSched sc;
+    sc.nstrips = cdiv(c->g.ny, kJacStripValid);
+    sc.first_int = 0; sc.n_int = 0;
+    for (int st = 0; st < sc.nstrips; ++st) {
+        const int jstrip = 1 - kJacStripMargin + st * kJacStripValid;
+        if (jstrip >= 2 && jstrip + kJacStripCols - 1 <= c->g.ny - 1) { if (!sc.n_int) sc.first_int = st; ++sc.n_int; }
+    }
+    const int n_edge = sc.nstrips - sc.n_int;
+    // one wave when the grid is big enough: every warp resident from start to end, and the slower edge
+    // strips (per-lane coefficients) get proportionally shorter chunks so that all warps finish together
+    const double edge_cost = 1.3;
+    int nch = (int)(c->jac_resident_warps[T] / (sc.n_int + edge_cost * n_edge));
+    const int min_rpc = 48;                            // bound the 2T-row warm-up overhead on small grids
+    nch = std::max(1, std::min(nch, std::max(1, rows / min_rpc)));
+    sc.nch_int = nch; sc.rpc_int = cdiv(rows, nch);
+    sc.nch_int = cdiv(rows, sc.rpc_int);
+    int nche = std::max(1, std::min((int)std::ceil(nch * edge_cost), std::max(1, rows / min_rpc)));
+    sc.rpc_edge = cdiv(rows, nche); sc.nch_edge = cdiv(rows, sc.rpc_edge);
+    const int nwarps = sc.n_int * sc.nch_int + n_edge * sc.nch_edge;
+    kern<<<cdiv(nwarps, kJacWarpsPerBlock), 32 * kJacWarpsPerBlock, 0, c->stream>>>(c->g, c->jac, sc, pin, pout, c->buf[BUF_RHS],
+                                                                                  c->in_a, c->in_b);
+    return launch_ok("k_jacobi_tb");
+}
+
+// nsweeps sweeps from the hoisted rhs, at most 5 per HBM pass; `frame`: keep ghost cells of p exact
+static int run_jacobi_tb(VofCtx* c, int nsweeps, bool frame) {
+    const int npass = cdiv(nsweeps, 5);
+    const int base = nsweeps / npass, extra = nsweeps % npass;
+    for (int k = 0; k < npass; ++k) {
+        const int T = base + (k < extra ? 1 : 0);
+        Span span_(c, VOF_K_JACOBI, frame ? 2 : 1);
+        int rc = VOF_OK;
+        switch (T) {
+            case 1: rc = launch_jacobi_tb<1>(c, c->p(), c->p_alt()); break;
+            case 2: rc = launch_jacobi_tb<2>(c, c->p(), c->p_alt()); break;
+            case 3: rc = launch_jacobi_tb<3>(c, c->p(), c->p_alt()); break;
+            case 4: rc = launch_jacobi_tb<4>(c, c->p(), c->p_alt()); break;
+            default: rc = launch_jacobi_tb<5>(c, c->p(), c->p_alt()); break;
+        }
+        if (rc != VOF_OK) return rc;
+        if (frame) {
+            const int nrow = c->all_b - c->all_a + 1;
+            const int lo_row = c->has_lo ? 0 - c->g.gi0 : -1, hi_row = c->has_hi ? c->g.nx + 1 - c->g.gi0 : -1;
+            const int n = nrow + (lo_row >= 0 ? c->g.ny + 2 : 0) + (hi_row >= 0 ? c->g.ny + 2 : 0);
+            k_copy_frame<<<cdiv(n, 128), 128, 0, c->stream>>>(c->g, c->p(), c->p_alt(), c->all_a, c->all_b, lo_row, hi_row);
+            TRY(launch_ok("k_copy_frame"));
+        }
+        c->p_cur ^= 1;
+    }
+    return VOF_OK;
+}
+
 static int run_project(VofCtx* c, bool inline_props) {
     Span span_(c, VOF_K_PROJECT);
     const int a = std::max(c->in_a, 1), b = c->in_b;
@@ -419,8 +513,6 @@ static int run_post(VofCtx* c) {
     return launch_ok("k_post_process_f");
 }
 
-#define TRY(x) do { int rc_ = (x); if (rc_ != VOF_OK) return rc_; } while (0)
-
 // ------------------------------------------------------------------------------------
 // one entry per reference kernel
 // ------------------------------------------------------------------------------------
@@ -444,6 +536,7 @@ extern "C" int vof2d_solve_p_jacobi(VofCtx* c, int nsweeps) {
     if (nsweeps == 1) return run_jacobi_sweep(c, 1);   // the reference's structure: rhs recomputed inside the sweep
     if (nsweeps == 0) return VOF_OK;
     TRY(run_rhs(c, false));
+    if (c->opt_jacobi_tb) return run_jacobi_tb(c, nsweeps, true);
     for (int s = 0; s < nsweeps; ++s) TRY(run_jacobi_sweep(c, 0));
     return VOF_OK;
 }
@@ -484,7 +577,8 @@ static int step_impl(VofCtx* c, int istep, unsigned flags) {
     TRY(run_advect(c, true));
     TRY(run_set_bc(c, mask));
     TRY(run_rhs(c, true));
-    for (int s = 0; s < c->P.n_jacobi; ++s) TRY(run_jacobi_sweep(c, 0));
+    if (c->opt_jacobi_tb && c->P.n_jacobi > 0) TRY(run_jacobi_tb(c, c->P.n_jacobi, false));
+    else for (int s = 0; s < c->P.n_jacobi; ++s) TRY(run_jacobi_sweep(c, 0));
     TRY(run_project(c, true));
     TRY(run_set_bc(c, mask));
     if (istep % 2 == 0) { TRY(run_fct_y(c, false)); TRY(run_fct_x(c, true)); }
@@ -710,5 +804,20 @@ extern "C" int vof2d_profile_read(VofCtx* c, int kind, double* ms_total, int64_t
     }
     if (ms_total) *ms_total = tot;
     if (spans) *spans = n;
+    return VOF_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// tuning knobs (A/B measurements; defaults are the fast paths)
+// ------------------------------------------------------------------------------------
+extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
+    CHECK_CTX(c);
+    switch (option) {
+        case VOF_OPT_JACOBI_TB: c->opt_jacobi_tb = value != 0; break;
+        default: return fail(VOF_EINVAL, "unknown option %d", option);
+    }
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 4; ++b)
+            if (c->graph[a][b]) { cudaGraphExecDestroy(c->graph[a][b]); c->graph[a][b] = nullptr; }
     return VOF_OK;
 }

@@ -237,6 +237,9 @@ class VofSolver2D:
     def state(self):
         return {k: getattr(self, k).to_numpy() for k in self.FIELDS}
 
+    def set_option(self, option: int, value: int):
+        check(self._L.vof2d_set_option(self._h, int(option), int(value)))
+
     # ---- measurement support
     def launch_count(self):
         return int(self._L.vof2d_launch_count(self._h))
