@@ -12,6 +12,7 @@
 
 #include "vof2d_kernels.cuh"
 #include "vof2d_jacobi_tb.cuh"
+#include "vof2d_fct.cuh"
 
 using namespace vof;
 
@@ -84,6 +85,7 @@ struct VofCtx {
     // CUDA graphs of two consecutive steps, keyed by parity of the first istep and flags
     cudaGraphExec_t graph[2][4];
     long long graph_launches[2][4];
+    FctC fctx, fcty;           // constants of the FCT sweeps
     JacTB jac;                 // constants of the temporally blocked Jacobi
     int jac_resident_warps[6]; // warps of k_jacobi_tb<T> resident on the whole GPU, by T
     int opt_jacobi_tb;         // 1: temporal blocking (default), 0: one launch per sweep
@@ -98,6 +100,14 @@ struct VofCtx {
     float* p() { return buf[p_cur ? BUF_P1 : BUF_P0]; }
     float* p_alt() { return buf[p_cur ? BUF_P0 : BUF_P1]; }
 };
+
+static ConstDiv make_const_div(float b) {
+    ConstDiv d;
+    d.b = b; d.bd = (double)b;
+    d.rd = 1.0 / d.bd;            // RN64(1/b)
+    d.r = (float)d.rd;            // RN32(1/b) up to double rounding; the exhaustive device check is the proof
+    return d;
+}
 
 static size_t field_stride_bytes(int nrows, int pitch) {
     size_t b = (size_t)nrows * pitch * sizeof(float);
@@ -212,9 +222,17 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
                 volatile float sum = ae + aw; sum = sum + an; sum = sum + as;
                 j.ap[ic][jc2] = -1.0f * sum;
             }
-        j.rap[0] = (float)(1.0 / (double)j.ap[0][0]);
-        j.rap[1] = (float)(1.0 / (double)j.ap[0][1]);
+        j.dv[0] = make_const_div(j.ap[0][0]);
+        j.dv[1] = make_const_div(j.ap[0][1]);
         j.fast_div_ok = 0;
+    }
+    {
+        FctC f{};
+        f.dt = k.dt; f.dx = k.dx; f.dy = k.dy; f.dxdy = k.dxdy;
+        f.d_dxdy = make_const_div(k.dxdy); f.d_dy = make_const_div(k.dy);
+        f.fast_div_ok = 0;
+        c->fctx = f; c->fctx.dtd = k.dtdy;     // 2dvof.py:324
+        c->fcty = f; c->fcty.dtd = k.dtdx;     // 2dvof.py:388
     }
     c->opt_jacobi_tb = 1;
     c->sm_count = prop.multiProcessorCount;
@@ -248,13 +266,19 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     {   // prove the reciprocal division exact for this diagonal: every fp32 numerator against __fdiv_rn
         unsigned long long* bad = &c->diag->courant_count;
         CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
-        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->jac.ap[0][0], c->jac.rap[0], bad);
-        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->jac.ap[0][1], c->jac.rap[1], bad);
+        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->jac.dv[0], bad);
+        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->jac.dv[1], bad);
         unsigned long long h = 1;
         CU(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
         c->jac.fast_div_ok = (h == 0);
+        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->fctx.d_dxdy, bad);
+        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->fctx.d_dy, bad);
+        CU(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
+        c->fctx.fast_div_ok = c->fcty.fast_div_ok = (h == 0);
     }
     c->ev_pool = new std::vector<cudaEvent_t>();
     c->spans = new std::vector<ProfSpan>();
@@ -336,7 +360,7 @@ struct Span {
 };
 
 constexpr int kRowsPerBlock = 32;   // rows marched by one block of the streaming kernels
-constexpr int kFctRows = 64;        // x-sweep chunk (6 warm-up rows are re-read per chunk)
+constexpr int kFctRows = 96;        // x-sweep chunk (6 warm-up rows are re-read per chunk)
 
 static unsigned bc_mask_all = 31u;
 
@@ -420,23 +444,14 @@ static int launch_jacobi_tb(VofCtx* c, const float* pin, float* pout) {
     }
     JacSched sc;
     sc.nstrips = cdiv(c->g.ny, kJacStripValid);
-    sc.first_int = 0; sc.n_int = 0;
-    for (int st = 0; st < sc.nstrips; ++st) {
-        const int jstrip = 1 - kJacStripMargin + st * kJacStripValid;
-        if (jstrip >= 2 && jstrip + kJacStripCols - 1 <= c->g.ny - 1) { if (!sc.n_int) sc.first_int = st; ++sc.n_int; }
-    }
-    const int n_edge = sc.nstrips - sc.n_int;
-    // one wave when the grid is big enough: every warp resident from start to end, and the slower edge
-    // strips (per-lane coefficients) get proportionally shorter chunks so that all warps finish together
-    const double edge_cost = 1.3;
-    int nch = (int)(c->jac_resident_warps[T] / (sc.n_int + edge_cost * n_edge));
-    const int min_rpc = 48;                            // bound the 2T-row warm-up overhead on small grids
-    nch = std::max(1, std::min(nch, std::max(1, rows / min_rpc)));
-    sc.nch_int = nch; sc.rpc_int = cdiv(rows, nch);
-    sc.nch_int = cdiv(rows, sc.rpc_int);
-    int nche = std::max(1, std::min((int)std::ceil(nch * edge_cost), std::max(1, rows / min_rpc)));
-    sc.rpc_edge = cdiv(rows, nche); sc.nch_edge = cdiv(rows, sc.rpc_edge);
-    const int nwarps = sc.n_int * sc.nch_int + n_edge * sc.nch_edge;
+    // items small enough that the queue balances data-dependent costs (several items per resident warp),
+    // large enough that the 2T warm-up rows of an item stay a small fraction
+    sc.rpc = std::min(rows, std::max(16 * T, 48));
+    sc.nchunks = cdiv(rows, sc.rpc);
+    sc.counter = &c->diag->queue;
+    const int nitems = sc.nstrips * sc.nchunks;
+    const int nwarps = std::min(nitems, c->jac_resident_warps[T]);
+    CU(cudaMemsetAsync(sc.counter, 0, sizeof(unsigned int), c->stream));
     kern<<<cdiv(nwarps, kJacWarpsPerBlock), 32 * kJacWarpsPerBlock, 0, c->stream>>>(c->g, c->jac, sc, pin, pout, c->buf[BUF_RHS],
                                                                                   c->in_a, c->in_b);
     return launch_ok("k_jacobi_tb");
@@ -487,22 +502,26 @@ static int run_project(VofCtx* c, bool inline_props) {
 static int run_fct_x(VofCtx* c, bool post) {
     Span span_(c, VOF_K_FCT_X);
     const int rows = c->in_b - c->in_a + 1;
-    dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, kFctRows));
-    if (post) k_fct_x<true><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, kFctRows);
-    else k_fct_x<false><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, kFctRows);
+    const int nstrips = cdiv(c->g.ny + 1, 128);
+    const int nwarps = nstrips * cdiv(rows, kFctRows);
+    dim3 grid(cdiv(nwarps, kFctXWarps));
+    if (post) k_fct_x4<true><<<grid, 32 * kFctXWarps, 0, c->stream>>>(c->g, c->fctx, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, kFctRows, nstrips);
+    else k_fct_x4<false><<<grid, 32 * kFctXWarps, 0, c->stream>>>(c->g, c->fctx, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, kFctRows, nstrips);
     c->F_cur ^= 1;
-    return launch_ok("k_fct_x");
+    return launch_ok("k_fct_x4");
 }
 
 static int run_fct_y(VofCtx* c, bool post) {
     Span span_(c, VOF_K_FCT_Y);
-    constexpr int TR = 4, TJ = 256;
     const int rows = c->all_b - c->all_a + 1;
-    dim3 grid(cdiv(c->g.ny, TJ), cdiv(rows, TR));
-    if (post) k_fct_y<true, TR, TJ><<<grid, 256, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b);
-    else k_fct_y<false, TR, TJ><<<grid, 256, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b);
+    const int nstrips = cdiv(c->g.ny + 1, kFctYValid);
+    const int rpw = 16;
+    const int nwarps = nstrips * cdiv(rows, rpw);
+    dim3 grid(cdiv(nwarps, kFctYWarps));
+    if (post) k_fct_y4<true><<<grid, 32 * kFctYWarps, 0, c->stream>>>(c->g, c->fcty, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b, rpw, nstrips);
+    else k_fct_y4<false><<<grid, 32 * kFctYWarps, 0, c->stream>>>(c->g, c->fcty, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b, rpw, nstrips);
     c->F_cur ^= 1;
-    return launch_ok("k_fct_y");
+    return launch_ok("k_fct_y4");
 }
 
 static int run_post(VofCtx* c) {

@@ -1,0 +1,256 @@
+// Zalesak/Rudman FCT sweeps (2dvof.py:321-448), instruction-lean versions.
+//
+// Both sweeps are issue-bound, not HBM-bound, when written naively (exact IEEE divisions: six per
+// cell).  These kernels keep the arithmetic bit-identical to the reference's expressions and cut the
+// instruction count by
+//   * 4 columns per lane (one LDG.128 / STG.128 per lane per row and per field);
+//   * computing each face flux once (the reference recomputes it in loops 1 and 2 and from both sides);
+//   * exact short-cuts that skip divisions whose result is known: a face whose two cells hold the same
+//     F has zero antidiffusive flux, so away from the interface the limiter ratios, the face limiter
+//     and the corrective update are skipped (x - 0 = x, 0 / y = 0 exactly);  min(1, q/p) = 1 when
+//     q >= p > 0;
+//   * division by the constants dx*dy and dy through their correctly rounded reciprocals plus one FMA
+//     residual correction (verified exhaustively at context creation, see vof2d_jacobi_tb.cuh).
+// x-sweep: a lane owns 4 columns and marches up a chunk of rows with the whole dependency chain in
+// registers (radius 3 along i).  y-sweep: a warp owns a strip of 128 columns of one row at a time and
+// exchanges the radius-3 chain with its neighbour lanes by shuffles (120 of 128 columns are stored).
+#pragma once
+#include "vof2d_jacobi_tb.cuh"
+#include "vof_common.cuh"
+
+namespace vof {
+
+struct FctC {
+    float dt, dx, dy, dxdy, dtd;   // dtd = dt*dy (x-sweep) or dt*dx (y-sweep), double-folded
+    ConstDiv d_dxdy, d_dy;         // exact division by the constants dx*dy and dy
+    int fast_div_ok;
+};
+
+__device__ __forceinline__ float fdiv_const(float t, const ConstDiv& d, bool fast) {
+    return fast ? div_by_const(t, d) : t / d.b;
+}
+
+// one face: low-order (donor) flux and antidiffusive flux a = downwind - donor   (2dvof.py:325-326, 342-348)
+__device__ __forceinline__ void fct_face(float vel, float F_m, float F_c, const FctC& c, float& lo, float& a) {
+    const float vd = vel * c.dt;
+    const float Fl = vel >= 0.0f ? F_m : F_c;
+    const float Fh = vel <= 0.0f ? F_m : F_c;
+    lo = vd * Fl;
+    a = vd * Fh - lo;
+}
+
+// transported-diffused value (2dvof.py:329-331); `interior` = the cell is in the global interior
+__device__ __forceinline__ float fct_ftd2(float F_c, float lo_c, float lo_p, float dv, bool interior, const FctC& c) {
+    const float s = lo_c - lo_p;
+    float t = F_c;
+    if (s != 0.0f) t = F_c + fdiv_const(s * c.dy, c.d_dxdy, c.fast_div_ok);   // F + (+-0) = F otherwise
+    float r = 0.0f;
+    if (t != 0.0f) {                                   // 0 * dx * dy / dv = 0
+        r = ((t * c.dx) * c.dy) / dv;
+        if (r > 1.0f || r < 0.0f) r = var01(r);
+    }
+    return interior ? r : 0.0f;
+}
+
+// limiter ratios of one cell (2dvof.py:334-335, 352-363); all-zero antidiffusive fluxes give 0, 0
+__device__ __forceinline__ void fct_ratios2(float td_m, float td_c, float td_p, float a_c, float a_p, bool interior,
+                                            const FctC& c, float& rp, float& rm) {
+    rp = 0.0f; rm = 0.0f;
+    if (interior && (a_c != 0.0f || a_p != 0.0f)) {
+        const float pp = fmaxf(0.0f, a_c) - fminf(0.0f, a_p);
+        const float pm = fmaxf(0.0f, a_p) - fminf(0.0f, a_c);
+        if (pp > 0.0f) {
+            const float fmax = fmaxf(fmaxf(td_c, td_m), td_p);
+            const float qp = (fmax - td_c) * c.dx;
+            rp = qp >= pp ? 1.0f : qp / pp;            // min(1, q/p) = 1 whenever q >= p > 0
+        }
+        if (pm > 0.0f) {
+            const float fmin = fminf(fminf(td_c, td_m), td_p);
+            const float qm = (td_c - fmin) * c.dx;
+            rm = qm >= pm ? 1.0f : qm / pm;
+        }
+    }
+}
+
+// face limiter (2dvof.py:366-369); irrelevant (multiplied by a = 0) when the face carries no flux
+__device__ __forceinline__ float fct_cface2(float a_f, float rp_m, float rm_m, float rp_c, float rm_c, bool valid_face) {
+    return valid_face ? (a_f >= 0.0f ? fminf(rp_c, rm_m) : fminf(rp_m, rm_c)) : 0.0f;
+}
+
+// corrective update + clamp (2dvof.py:377-382) [+ post_process_f, 452-455]
+template <bool POST>
+__device__ __forceinline__ float fct_update2(float td_c, float a_c, float c_c, float a_p, float c_p, float dv, const FctC& c) {
+    float fn = td_c;
+    if (a_c != 0.0f || a_p != 0.0f) {
+        const float t = a_p * c_p - a_c * c_c;
+        if (t != 0.0f) fn = td_c - ((fdiv_const(t, c.d_dy, c.fast_div_ok) * c.dx) * c.dy) / dv;
+    }
+    float f = var01(fn);
+    if (POST) f = var01(f);
+    return f;
+}
+
+// ======================================================================================
+// x-sweep: lane = 4 columns, marches rows ia-2 .. ib+3, output row = row loaded 3 iterations ago
+// ======================================================================================
+constexpr int kFctXWarps = 4;
+
+template <bool POST>
+__global__ void __launch_bounds__(32 * kFctXWarps)
+k_fct_x4(Grid g, FctC c, const float* __restrict__ Fin, const float* __restrict__ u, float* __restrict__ Fout,
+         int r0, int r1, int rows_per_chunk, int nstrips) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kFctXWarps + (threadIdx.x >> 5);
+    const int strip = w % nstrips, chunk = w / nstrips;
+    const int ia = r0 + chunk * rows_per_chunk;
+    if (ia > r1) return;
+    const int ib = min(r1, ia + rows_per_chunk - 1);
+    const int jl = 1 + 128 * strip + 4 * lane;
+    if (jl > g.ny + 1) return;
+    const int P = g.pitch, last = g.nrows - 1;
+    const float* Fc = Fin + jl;
+    const float* uc = u + jl;
+    float* Fo = Fout + jl;
+    auto ld4 = [&](const float* base, int i) { return *reinterpret_cast<const float4*>(base + (size_t)min(max(i, 0), last) * P); };
+    const bool lo_wall = g.gi0 + ia == 1, hi_wall = g.gi0 + ib == g.nx;
+    // ghost rows / ghost column 0 pass through (the sweep never writes them; out-of-place needs the copy)
+    if (lo_wall) *reinterpret_cast<float4*>(Fo + (size_t)(ia - 1) * P) = ld4(Fc, ia - 1);
+    if (hi_wall) *reinterpret_cast<float4*>(Fo + (size_t)(ib + 1) * P) = ld4(Fc, ib + 1);
+    if (strip == 0 && lane == 0) {
+        for (int i = ia - (lo_wall ? 1 : 0); i <= ib + (hi_wall ? 1 : 0); ++i) Fout[(size_t)i * P] = Fin[(size_t)i * P];
+    }
+    bool colin[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) colin[k] = jl + k <= g.ny;
+
+    float F1[4], u1[4], lo1[4], a1[4], a2[4], a3[4], td1[4], td2[4], td3[4], dv1[4], dv2[4], dv3[4], rp2[4], rm2[4], c2[4];
+    float Fk[4], uk[4];
+    {
+        const float4 f = ld4(Fc, ia - 3), fk = ld4(Fc, ia - 2), uu = ld4(uc, ia - 2);
+        F1[0] = f.x; F1[1] = f.y; F1[2] = f.z; F1[3] = f.w;
+        Fk[0] = fk.x; Fk[1] = fk.y; Fk[2] = fk.z; Fk[3] = fk.w;
+        uk[0] = uu.x; uk[1] = uu.y; uk[2] = uu.z; uk[3] = uu.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        u1[k] = 0.f; lo1[k] = 0.f; a1[k] = a2[k] = a3[k] = 0.f; td1[k] = td2[k] = td3[k] = 0.f;
+        dv1[k] = dv2[k] = dv3[k] = 1.f; rp2[k] = rm2[k] = 0.f; c2[k] = 0.f;
+    }
+    for (int k = ia - 2; k <= ib + 3; ++k) {
+        const float4 Fn = ld4(Fc, k + 1), un = ld4(uc, k + 1);          // prefetch the next row
+        const int gk = g.gi0 + k;
+        const bool in1 = gk - 1 >= 1 && gk - 1 <= g.nx;                 // cell k-1 interior
+        const bool in2 = gk - 2 >= 1 && gk - 2 <= g.nx;                 // cell k-2 interior
+        const bool face2 = gk - 2 >= 2 && gk - 2 <= g.nx + 1;           // face k-2 has a limiter (cx[1] is never written)
+        const int io = k - 3;
+        const bool store = io >= ia && io <= ib;                        // rows ia..ib are interior by construction
+        float out[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float lo0, a0;
+            fct_face(uk[q], F1[q], Fk[q], c, lo0, a0);                                   // face k
+            const float dv_n = c.dxdy - c.dtd * (uk[q] - u1[q]);                         // cell k-1
+            const float td_n = fct_ftd2(F1[q], lo1[q], lo0, dv_n, in1, c);
+            td3[q] = td2[q]; td2[q] = td1[q]; td1[q] = td_n;
+            dv3[q] = dv2[q]; dv2[q] = dv1[q]; dv1[q] = dv_n;
+            float rp_n, rm_n;
+            fct_ratios2(td3[q], td2[q], td1[q], a2[q], a1[q], in2, c, rp_n, rm_n);       // cell k-2
+            const float c_n = fct_cface2(a2[q], rp2[q], rm2[q], rp_n, rm_n, face2);      // face k-2
+            out[q] = fct_update2<POST>(td3[q], a3[q], c2[q], a2[q], c_n, dv3[q], c);     // cell k-3
+            rp2[q] = rp_n; rm2[q] = rm_n; c2[q] = c_n;
+            a3[q] = a2[q]; a2[q] = a1[q]; a1[q] = a0; lo1[q] = lo0;
+            F1[q] = Fk[q]; u1[q] = uk[q];
+        }
+        if (store) {
+            if (colin[3]) {
+                *reinterpret_cast<float4*>(Fo + (size_t)io * P) = make_float4(out[0], out[1], out[2], out[3]);
+            } else {                             // pass-through for columns past ny (ghost ny+1, padding)
+                const float4 old = ld4(Fc, io);
+                *reinterpret_cast<float4*>(Fo + (size_t)io * P) =
+                    make_float4(colin[0] ? out[0] : old.x, colin[1] ? out[1] : old.y, colin[2] ? out[2] : old.z, old.w);
+            }
+        }
+        Fk[0] = Fn.x; Fk[1] = Fn.y; Fk[2] = Fn.z; Fk[3] = Fn.w;
+        uk[0] = un.x; uk[1] = un.y; uk[2] = un.z; uk[3] = un.w;
+    }
+}
+
+// ======================================================================================
+// y-sweep: warp = strip of 128 columns (lanes 1..30 store), one row per iteration
+// ======================================================================================
+constexpr int kFctYWarps = 4;
+constexpr int kFctYValid = 120;
+
+template <bool POST>
+__global__ void __launch_bounds__(32 * kFctYWarps)
+k_fct_y4(Grid g, FctC c, const float* __restrict__ Fin, const float* __restrict__ v, float* __restrict__ Fout,
+         int r0, int r1, int rows_per_warp, int nstrips) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kFctYWarps + (threadIdx.x >> 5);
+    const int strip = w % nstrips, chunk = w / nstrips;
+    const int ia = r0 + chunk * rows_per_warp;
+    if (ia > r1) return;
+    const int ib = min(r1, ia + rows_per_warp - 1);
+    const int jl = 1 - 4 + kFctYValid * strip + 4 * lane;     // == 1 (mod 4)
+    const bool active = jl <= g.ny + 1;
+    const bool store_lane = active && lane >= 1 && lane <= 30;
+    const int P = g.pitch;
+    const float* Fc = Fin + jl;
+    const float* vc = v + jl;
+    float* Fo = Fout + jl;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool cin[6];      // cells jl-1 .. jl+4 in the global interior
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cin[k] = jl - 1 + k >= 1 && jl - 1 + k <= g.ny;
+    bool fvalid[5];   // faces jl .. jl+4 carry a limiter (cy on face 1 is never written)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) fvalid[k] = jl + k >= 2 && jl + k <= g.ny + 1;
+
+    float4 Fq = active ? *reinterpret_cast<const float4*>(Fc + (size_t)ia * P) : zero4;
+    float4 vq = active ? *reinterpret_cast<const float4*>(vc + (size_t)ia * P) : zero4;
+    for (int i = ia; i <= ib; ++i) {
+        const float F[4] = {Fq.x, Fq.y, Fq.z, Fq.w}, vv[4] = {vq.x, vq.y, vq.z, vq.w};
+        if (i < ib && active) {                                        // prefetch the next row
+            Fq = *reinterpret_cast<const float4*>(Fc + (size_t)(i + 1) * P);
+            vq = *reinterpret_cast<const float4*>(vc + (size_t)(i + 1) * P);
+        }
+        const int gi = g.gi0 + i;
+        const bool rowin = gi >= 1 && gi <= g.nx;
+        const float F_m1 = __shfl_up_sync(0xffffffffu, F[3], 1);       // F[jl-1]
+        const float v_p4 = __shfl_down_sync(0xffffffffu, vv[0], 1);    // v[jl+4]
+        float lo[5], a[5];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fct_face(vv[k], k ? F[k - 1] : F_m1, F[k], c, lo[k], a[k]);
+        lo[4] = __shfl_down_sync(0xffffffffu, lo[0], 1);
+        a[4] = __shfl_down_sync(0xffffffffu, a[0], 1);
+        float dv[4], td[6];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            dv[k] = c.dxdy - c.dtd * ((k < 3 ? vv[k + 1] : v_p4) - vv[k]);
+            td[k + 1] = fct_ftd2(F[k], lo[k], lo[k + 1], dv[k], cin[k + 1], c);
+        }
+        td[0] = __shfl_up_sync(0xffffffffu, td[4], 1);
+        td[5] = __shfl_down_sync(0xffffffffu, td[1], 1);
+        float rp[5], rm[5];   // index k+1 = cell jl+k; index 0 = cell jl-1
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fct_ratios2(td[k], td[k + 1], td[k + 2], a[k], a[k + 1], cin[k + 1], c, rp[k + 1], rm[k + 1]);
+        rp[0] = __shfl_up_sync(0xffffffffu, rp[4], 1);
+        rm[0] = __shfl_up_sync(0xffffffffu, rm[4], 1);
+        float cf[5];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cf[k] = fct_cface2(a[k], rp[k], rm[k], rp[k + 1], rm[k + 1], fvalid[k]);
+        cf[4] = __shfl_down_sync(0xffffffffu, cf[0], 1);
+        if (store_lane) {
+            float out[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float f = fct_update2<POST>(td[k + 1], a[k], cf[k], a[k + 1], cf[k + 1], dv[k], c);
+                out[k] = (rowin && cin[k + 1]) ? f : F[k];             // ghost rows / columns pass through
+            }
+            *reinterpret_cast<float4*>(Fo + (size_t)i * P) = make_float4(out[0], out[1], out[2], out[3]);
+        }
+        if (strip == 0 && lane == 0) Fout[(size_t)i * P] = F[3];       // ghost column 0 (jl + 3 == 0)
+    }
+}
+
+}  // namespace vof

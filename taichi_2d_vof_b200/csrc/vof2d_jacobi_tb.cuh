@@ -11,29 +11,36 @@
 //     (112 of 128 columns are stored) and chunks by 2 x T rows -- redundant work instead of
 //     any inter-warp communication.
 // Walls are zeroed coefficients (2dvof.py:258-262).  Strips that touch no j-wall use literal
-// constants; the two edge strips carry per-lane coefficients (EDGE = true) and get shorter chunks
-// so that every warp of the single wave finishes together.  Rows that touch an i-wall (2 of nx)
-// and ghost rows go through one out-of-line general routine.
+// constants; the two edge strips carry per-lane coefficients (EDGE = true).  Rows that touch an
+// i-wall (2 of nx) and ghost rows go through one out-of-line general routine.  Persistent warps
+// pull (strip, chunk) items from a queue, because the cost of an item is data dependent.
 // Results are bit-identical to T single sweeps of k_jacobi: same expressions, same order; the
 // division by the (constant) diagonal uses its correctly rounded reciprocal plus one exact
 // FMA residual correction, which returns the correctly rounded quotient (verified against
-// __fdiv_rn for EVERY fp32 numerator in [2^-100, 2^100] when the context is created; smaller
-// numerators take the IEEE path).
+// __fdiv_rn for EVERY fp32 numerator up to 2^100 when the context is created; numerators below
+// 2^-100 run the same scheme in fp64).
 #pragma once
 #include "vof_common.cuh"
 
 namespace vof {
 
-struct JacTB {
-    float cx, cy;          // dxi^2, dyi^2 (2dvof.py:258-261)
-    float ap[2][2];        // -(ae+aw+an+as) by [row touches an i-wall][column touches a j-wall]
-    float rap[2];          // RN(1 / ap[0][jc])
-    int fast_div_ok;       // reciprocal division validated for ap[0][0] and ap[0][1]
-};
-
 constexpr float kTinyNumerator = 7.8886090522101181e-31f;   // 2^-100
 
-__device__ __noinline__ float div_ieee(float t, float b) { return __fdiv_rn(t, b); }
+// A constant divisor with its reciprocals.  Fast path (fp32): q = RN(t r), q' = RN(q + (t - q b) r) is the
+// correctly rounded quotient [Markstein] unless the residual underflows (|t| < 2^-100).  Slow path (tiny t,
+// usually a subnormal quotient): the same two-step scheme in fp64 gives RN64(t / b) -- nothing underflows
+// there -- and RN32(RN64(x)) == RN32(x) for a quotient because 53 >= 2*24 + 2 (double rounding is innocuous;
+// holds for subnormal fp32 results too).  Both paths are checked against __fdiv_rn for every fp32 t.
+struct ConstDiv {
+    float b, r;        // divisor, RN32(1/b)
+    double bd, rd;     // divisor, RN64(1/b)
+};
+__device__ __forceinline__ float div_slow(float t, const ConstDiv& d) {
+    const double td = (double)t;
+    const double q = td * d.rd;
+    const double rem = __fma_rn(-q, d.bd, td);
+    return __double2float_rn(__fma_rn(rem, d.rd, q));
+}
 
 // correctly rounded t / b from r = RN(1/b): q = RN(t r); q' = RN(q + (t - q b) r)   [Markstein]
 // valid for t = 0 (sign included) and 2^-100 <= |t| <= 2^100; see div_needs_ieee
@@ -43,14 +50,21 @@ __device__ __forceinline__ float div_by_const_core(float t, float b, float r) {
     return __fmaf_rn(rem, r, q);
 }
 __device__ __forceinline__ bool div_needs_ieee(float t) { return fabsf(t) < kTinyNumerator && t != 0.0f; }
-__device__ __forceinline__ float div_by_const(float t, float b, float r) {
-    float q = div_by_const_core(t, b, r);
-    if (div_needs_ieee(t)) q = div_ieee(t, b);   // the residual would underflow: IEEE path
+__device__ __forceinline__ float div_by_const(float t, const ConstDiv& d) {
+    float q = div_by_const_core(t, d.b, d.r);
+    if (div_needs_ieee(t)) q = div_slow(t, d);   // the fp32 residual would underflow
     return q;
 }
 
+struct JacTB {
+    float cx, cy;          // dxi^2, dyi^2 (2dvof.py:258-261)
+    float ap[2][2];        // -(ae+aw+an+as) by [row touches an i-wall][column touches a j-wall]
+    ConstDiv dv[2];        // division by ap[0][jc]
+    int fast_div_ok;       // reciprocal division validated for ap[0][0] and ap[0][1]
+};
+
 // exhaustive check of div_by_const against IEEE division: every fp32 bit pattern
-__global__ void k_check_div_by_const(float b, float r, unsigned long long* mismatches) {
+__global__ void k_check_div_by_const(ConstDiv d, unsigned long long* mismatches) {
     const unsigned long long n = 1ull << 32;
     unsigned long long bad = 0;
     for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n;
@@ -58,7 +72,7 @@ __global__ void k_check_div_by_const(float b, float r, unsigned long long* misma
         const float t = __uint_as_float((unsigned)k);
         const float at = fabsf(t);
         if (!(at <= 1.2676506002282294e30f)) continue;       // 2^100; also skips NaN
-        const float a = div_by_const(t, b, r), e = __fdiv_rn(t, b);
+        const float a = div_by_const(t, d), e = __fdiv_rn(t, d.b);
         bad += (__float_as_uint(a) != __float_as_uint(e));
     }
     if (bad) atomicAdd(mismatches, bad);
@@ -72,7 +86,8 @@ struct JacPipe {
 
 // per-lane wall coefficients of an edge strip (unused by interior strips)
 struct JacEdge {
-    float an[4], as[4], ap[4], rap[4];
+    float an[4], as[4];
+    int cls[4];            // 1: the column touches a j-wall (diagonal ap[0][1])
     bool colin[4];
 };
 
@@ -145,17 +160,18 @@ __device__ __forceinline__ void jac_step(JacPipe<T>& S, const JacEdge& E, const 
                 bool slow = false;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    out[k] = div_by_const_core(t[k], EDGE ? E.ap[k] : jc.ap[0][0], EDGE ? E.rap[k] : jc.rap[0]);
+                    const ConstDiv& d = jc.dv[EDGE ? E.cls[k] : 0];
+                    out[k] = div_by_const_core(t[k], d.b, d.r);
                     slow = slow || div_needs_ieee(t[k]);
                 }
                 if (slow) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (div_needs_ieee(t[k])) out[k] = div_ieee(t[k], EDGE ? E.ap[k] : jc.ap[0][0]);
+                        if (div_needs_ieee(t[k])) out[k] = div_slow(t[k], jc.dv[EDGE ? E.cls[k] : 0]);
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) out[k] = t[k] / (EDGE ? E.ap[k] : jc.ap[0][0]);
+                for (int k = 0; k < 4; ++k) out[k] = t[k] / jc.dv[EDGE ? E.cls[k] : 0].b;
             }
             if (EDGE) {
 #pragma unroll
@@ -181,11 +197,9 @@ constexpr int kJacStripMargin = 8;      // columns given up at each strip edge (
 constexpr int kJacStripValid = kJacStripCols - 2 * kJacStripMargin;
 constexpr int kJacWarpsPerBlock = 4;
 
-struct JacSched {          // warp -> (strip, chunk): interior strips first, then the (slower) edge strips
-    int nstrips;           // all strips
-    int n_int, first_int;  // interior strips are first_int .. first_int + n_int - 1
-    int nch_int, rpc_int;  // chunks per interior strip, rows per chunk
-    int nch_edge, rpc_edge;
+struct JacSched {          // work item -> (strip, chunk); warps pull items from a global counter
+    int nstrips, nchunks, rpc;
+    unsigned int* counter; // zeroed by the host before the launch
 };
 
 template <int T, bool EDGE, bool FAST_DIV>
@@ -209,9 +223,7 @@ __device__ __forceinline__ void jac_run(const Grid& g, const JacTB& jc, const fl
             const int j = jl + k;
             E.an[k] = (j != g.ny) ? jc.cy : 0.0f;
             E.as[k] = (j != 1) ? jc.cy : 0.0f;
-            const int c2 = (j == 1 || j == g.ny) ? 1 : 0;
-            E.ap[k] = jc.ap[0][c2];
-            E.rap[k] = jc.rap[c2];
+            E.cls[k] = (j == 1 || j == g.ny) ? 1 : 0;
             E.colin[k] = j >= 1 && j <= g.ny;
         }
     }
@@ -241,26 +253,22 @@ k_jacobi_tb(Grid g, JacTB jc, JacSched sc, const float* __restrict__ p, float* _
             const float* __restrict__ rhs, int r0, int r1) {
     static_assert(T >= 1 && T <= kJacStripMargin, "strip margin must cover the sweeps of one pass");
     const int lane = threadIdx.x & 31;
-    int w = blockIdx.x * kJacWarpsPerBlock + (threadIdx.x >> 5);
-    int strip, chunk, rpc;
-    const int n_int_warps = sc.n_int * sc.nch_int;
-    if (w < n_int_warps) {
-        strip = sc.first_int + w % sc.n_int; chunk = w / sc.n_int; rpc = sc.rpc_int;
-    } else {
-        w -= n_int_warps;
-        const int n_edge = sc.nstrips - sc.n_int;
-        if (n_edge <= 0 || w >= n_edge * sc.nch_edge) return;
-        const int e = w % n_edge;            // edge strips are those outside [first_int, first_int + n_int)
-        strip = e < sc.first_int ? e : e + sc.n_int;
-        chunk = w / n_edge; rpc = sc.rpc_edge;
+    const int nitems = sc.nstrips * sc.nchunks;
+    // persistent warps + work queue: the cost of an item is data dependent (tiny numerators take the fp64
+    // division) and edge strips are slower, so a static one-item-per-warp wave would wait for the slowest warp
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = (int)atomicAdd(sc.counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nitems) break;
+        const int strip = item % sc.nstrips, chunk = item / sc.nstrips;
+        const int ra = r0 + chunk * sc.rpc;
+        const int rb = min(r1, ra + sc.rpc - 1);
+        const int jstrip = 1 - kJacStripMargin + strip * kJacStripValid;   // == 1 (mod 4): float4-aligned
+        const bool strip_interior = jstrip >= 2 && jstrip + kJacStripCols - 1 <= g.ny - 1;
+        if (strip_interior) jac_run<T, false, FAST_DIV>(g, jc, p, pout, rhs, ra, rb, jstrip, lane);
+        else jac_run<T, true, FAST_DIV>(g, jc, p, pout, rhs, ra, rb, jstrip, lane);
     }
-    const int ra = r0 + chunk * rpc;
-    if (ra > r1) return;
-    const int rb = min(r1, ra + rpc - 1);
-    const int jstrip = 1 - kJacStripMargin + strip * kJacStripValid;   // == 1 (mod 4): float4-aligned
-    const bool strip_interior = jstrip >= 2 && jstrip + kJacStripCols - 1 <= g.ny - 1;
-    if (strip_interior) jac_run<T, false, FAST_DIV>(g, jc, p, pout, rhs, ra, rb, jstrip, lane);
-    else jac_run<T, true, FAST_DIV>(g, jc, p, pout, rhs, ra, rb, jstrip, lane);
 }
 
 // ghost cells of the field pass through a sweep unchanged; the pipeline above only stores columns of

@@ -622,6 +622,7 @@ struct Diag {
     unsigned int max_cfl_bits;
     unsigned int resid_bits;
     unsigned long long courant_count;
+    unsigned int queue;          // work-queue head of the persistent kernels
 };
 
 __global__ void __launch_bounds__(256)
