@@ -13,6 +13,7 @@
 #include "vof2d_kernels.cuh"
 #include "vof2d_jacobi_tb.cuh"
 #include "vof2d_fct.cuh"
+#include "vof2d_momentum.cuh"
 
 using namespace vof;
 
@@ -86,6 +87,7 @@ struct VofCtx {
     cudaGraphExec_t graph[2][4];
     long long graph_launches[2][4];
     FctC fctx, fcty;           // constants of the FCT sweeps
+    MomC mom;                  // constants of the momentum predictor
     JacTB jac;                 // constants of the temporally blocked Jacobi
     int jac_resident_warps[6]; // warps of k_jacobi_tb<T> resident on the whole GPU, by T
     int opt_jacobi_tb;         // 1: temporal blocking (default), 0: one launch per sweep
@@ -234,6 +236,7 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
         c->fctx = f; c->fctx.dtd = k.dtdy;     // 2dvof.py:324
         c->fcty = f; c->fcty.dtd = k.dtdx;     // 2dvof.py:388
     }
+    c->mom.k = k; c->mom.d_dx = make_const_div(k.dx); c->mom.d_dy = make_const_div(k.dy); c->mom.fast_div_ok = 0;
     c->opt_jacobi_tb = 1;
     c->sm_count = prop.multiProcessorCount;
     c->all_a = std::max(0, -g.gi0);
@@ -279,6 +282,12 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
         c->fctx.fast_div_ok = c->fcty.fast_div_ok = (h == 0);
+        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->mom.d_dx, bad);
+        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->mom.d_dy, bad);
+        CU(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
+        c->mom.fast_div_ok = (h == 0);
     }
     c->ev_pool = new std::vector<cudaEvent_t>();
     c->spans = new std::vector<ProfSpan>();
@@ -391,18 +400,21 @@ static int run_kappa(VofCtx* c) {
     return launch_ok("k_kappa");
 }
 
+constexpr int kMomRows = 64;       // rows marched by one warp of the momentum kernels
+
 static int run_advect(VofCtx* c, bool inline_props) {
     Span span_(c, VOF_K_ADVECT);
     const int a = std::max(c->in_a, 1), b = std::min(c->in_b, c->g.nrows - 2);
     const int rows = b - a + 1;
-    dim3 grid(cdiv(c->g.ny, kBlockJ), cdiv(rows, kRowsPerBlock));
+    const int nstrips = cdiv(c->g.ny, 128);
+    dim3 grid(cdiv(nstrips * cdiv(rows, kMomRows), kMomWarps));
     if (inline_props)
-        k_advect<true><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->buf[BUF_KAPPA], nullptr,
-                                                       nullptr, c->buf[BUF_US], c->buf[BUF_VS], a, b, kRowsPerBlock);
+        k_advect4<true><<<grid, 32 * kMomWarps, 0, c->stream>>>(c->g, c->mom, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->buf[BUF_KAPPA], nullptr,
+                                                              nullptr, c->buf[BUF_US], c->buf[BUF_VS], a, b, kMomRows, nstrips);
     else
-        k_advect<false><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->buf[BUF_KAPPA],
-                                                        c->buf[BUF_RHO], c->buf[BUF_NU], c->buf[BUF_US], c->buf[BUF_VS], a, b, kRowsPerBlock);
-    return launch_ok("k_advect");
+        k_advect4<false><<<grid, 32 * kMomWarps, 0, c->stream>>>(c->g, c->mom, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->buf[BUF_KAPPA],
+                                                               c->buf[BUF_RHO], c->buf[BUF_NU], c->buf[BUF_US], c->buf[BUF_VS], a, b, kMomRows, nstrips);
+    return launch_ok("k_advect4");
 }
 
 static int run_rhs(VofCtx* c, bool inline_props) {
@@ -489,14 +501,18 @@ static int run_project(VofCtx* c, bool inline_props) {
     Span span_(c, VOF_K_PROJECT);
     const int a = std::max(c->in_a, 1), b = c->in_b;
     const int rows = b - a + 1;
-    dim3 grid(cdiv(c->g.ny, kBlockJ), cdiv(rows, kRowsPerBlock));
+    const int nstrips = cdiv(c->g.ny, 128);
+    dim3 grid(cdiv(nstrips * cdiv(rows, kMomRows), kMomWarps));
     unsigned long long* cc = &c->diag->courant_count;
     CU(cudaMemsetAsync(cc, 0, sizeof(*cc), c->stream));
+    const float* rhoF = inline_props ? c->F() : c->buf[BUF_RHO];
     if (inline_props)
-        k_project<true><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->p(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_U], c->buf[BUF_V], cc, a, b, kRowsPerBlock, c->lo - c->g.gi0, c->hi - c->g.gi0);
+        k_project4<true><<<grid, 32 * kMomWarps, 0, c->stream>>>(c->g, c->k, rhoF, c->p(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_U], c->buf[BUF_V],
+                                                               cc, a, b, kMomRows, nstrips, c->lo - c->g.gi0, c->hi - c->g.gi0);
     else
-        k_project<false><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->buf[BUF_RHO], c->p(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_U], c->buf[BUF_V], cc, a, b, kRowsPerBlock, c->lo - c->g.gi0, c->hi - c->g.gi0);
-    return launch_ok("k_project");
+        k_project4<false><<<grid, 32 * kMomWarps, 0, c->stream>>>(c->g, c->k, rhoF, c->p(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_U], c->buf[BUF_V],
+                                                                cc, a, b, kMomRows, nstrips, c->lo - c->g.gi0, c->hi - c->g.gi0);
+    return launch_ok("k_project4");
 }
 
 static int run_fct_x(VofCtx* c, bool post) {

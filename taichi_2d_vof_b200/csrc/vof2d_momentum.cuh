@@ -1,0 +1,250 @@
+// Momentum predictor and projection (2dvof.py:206-233, 269-280), instruction-lean versions.
+//
+// Same pattern as the other kernels: a lane owns 4 consecutive columns (one LDG.128 per field per row),
+// a warp owns 128 aligned columns and marches up a chunk of rows; the i-neighbours of a row live in a
+// three-slot register ring (the loop is unrolled by 3, nothing is moved), the j-neighbours come from the
+// adjacent lanes by shuffle (the two lanes at the strip edge read their missing neighbour directly).
+// Arithmetic is the reference's, term for term; the only short-cut is exact: the CSF term is skipped
+// where F has no jump across the face (it is then +-0, and x + (+-0) = x).
+#pragma once
+#include "vof2d_jacobi_tb.cuh"
+#include "vof_common.cuh"
+
+namespace vof {
+
+constexpr int kMomWarps = 4;
+
+struct MomC {
+    Consts k;
+    ConstDiv d_dx, d_dy;   // exact division by the constants dx and dy (2dvof.py:213, 226)
+    int fast_div_ok;
+};
+
+// x[-1..4] of one row: [0] = left neighbour (column jl-1), [1..4] = own columns, [5] = right neighbour (jl+4)
+struct Row6 { float x[6]; };
+
+__device__ __forceinline__ void load_row6(Row6& r, const float* __restrict__ base, size_t off, int lane, bool active,
+                                          bool need_left, bool need_right) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) v = *reinterpret_cast<const float4*>(base + off);
+    r.x[1] = v.x; r.x[2] = v.y; r.x[3] = v.z; r.x[4] = v.w;
+    if (need_left) {
+        r.x[0] = __shfl_up_sync(0xffffffffu, v.w, 1);
+        if (lane == 0 && active) r.x[0] = base[off - 1];
+    }
+    if (need_right) {
+        r.x[5] = __shfl_down_sync(0xffffffffu, v.x, 1);
+        if (lane == 31 && active) r.x[5] = base[off + 4];
+    }
+}
+
+template <bool INLINE_PROPS>
+struct AdvState {
+    Row6 u[3], v[3];       // ring over rows i-1, i, i+1
+    Row6 F[3], kp[3];      // F and kappa: own columns + left neighbour
+    Row6 rho[3];           // rho: own columns + left neighbour
+    float nu[3][4];
+};
+
+template <bool INLINE_PROPS, int PH>
+__device__ __forceinline__ void adv_load(AdvState<INLINE_PROPS>& S, const MomC& c, const float* __restrict__ u,
+                                         const float* __restrict__ v, const float* __restrict__ F,
+                                         const float* __restrict__ kappa, const float* __restrict__ rho,
+                                         const float* __restrict__ nu, size_t off, int lane, bool active) {
+    load_row6(S.u[PH], u, off, lane, active, true, true);
+    load_row6(S.v[PH], v, off, lane, active, true, true);
+    load_row6(S.F[PH], F, off, lane, active, true, false);
+    load_row6(S.kp[PH], kappa, off, lane, active, true, false);
+    if (INLINE_PROPS) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) S.rho[PH].x[q] = rho_of(S.F[PH].x[q], c.k);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) S.nu[PH][q] = nu_of(S.F[PH].x[q + 1], c.k);
+    } else {
+        load_row6(S.rho[PH], rho, off, lane, active, true, false);
+        float4 n = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) n = *reinterpret_cast<const float4*>(nu + off);
+        S.nu[PH][0] = n.x; S.nu[PH][1] = n.y; S.nu[PH][2] = n.z; S.nu[PH][3] = n.w;
+    }
+}
+
+// row i = slot MID; writes u*(i, .) and v*(i, .)
+template <bool INLINE_PROPS, int PH>
+__device__ __forceinline__ void adv_row(const AdvState<INLINE_PROPS>& S, const MomC& c, float* __restrict__ us,
+                                        float* __restrict__ vs, size_t off, int gi, int jl, int nx, int ny) {
+    constexpr int P1 = PH, C = (PH + 2) % 3, M = (PH + 1) % 3;   // rows i+1, i, i-1
+    const Consts& k = c.k;
+    float ou[4], ov[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int e = q + 1;                      // index into Row6
+        const float u_c = S.u[C].x[e], v_c = S.v[C].x[e];
+        const float F_c = S.F[C].x[e], k_c = S.kp[C].x[e], rho_c = S.rho[C].x[e], nu_c = S.nu[C][q];
+        {   // ---- u*  (2dvof.py:208-220)
+            const float u_m = S.u[M].x[e], u_p = S.u[P1].x[e], u_jm = S.u[C].x[e - 1], u_jp = S.u[C].x[e + 1];
+            const float v_here = 0.25f * (((S.v[M].x[e] + S.v[M].x[e + 1]) + v_c) + S.v[C].x[e + 1]);
+            const float dudx = u_c > 0.0f ? (u_c - u_m) * k.dxi : (u_p - u_c) * k.dxi;
+            const float dudy = v_here > 0.0f ? (u_c - u_jm) * k.dyi : (u_jp - u_c) * k.dyi;
+            const float two_u = 2.0f * u_c;
+            float acc = (nu_c * ((u_m - two_u) + u_p)) * k.dxi2;
+            acc = acc + (nu_c * ((u_jm - two_u) + u_jp)) * k.dyi2;
+            acc = acc - u_c * dudx;
+            acc = acc - v_here * dudy;
+            acc = acc + k.gx;
+            const float dF = F_c - S.F[M].x[e];
+            if (dF != 0.0f) {                     // otherwise the CSF term is +-0
+                const float kappa_ave = (k_c + S.kp[M].x[e]) / 2.0f;
+                const float t = (k.neg_sigma * dF) * kappa_ave;
+                const float fx_kappa = c.fast_div_ok ? div_by_const(t, c.d_dx) : t / k.dx;
+                acc = acc + (fx_kappa * 2.0f) / (rho_c + S.rho[M].x[e]);
+            }
+            ou[q] = u_c + k.dt * acc;
+        }
+        {   // ---- v*  (2dvof.py:221-233)
+            const float v_m = S.v[M].x[e], v_p = S.v[P1].x[e], v_jm = S.v[C].x[e - 1], v_jp = S.v[C].x[e + 1];
+            const float u_here = 0.25f * (((S.u[C].x[e - 1] + u_c) + S.u[P1].x[e - 1]) + S.u[P1].x[e]);
+            const float dvdx = u_here > 0.0f ? (v_c - v_m) * k.dxi : (v_p - v_c) * k.dxi;
+            const float dvdy = v_c > 0.0f ? (v_c - v_jm) * k.dyi : (v_jp - v_c) * k.dyi;
+            const float two_v = 2.0f * v_c;
+            float acc = (nu_c * ((v_m - two_v) + v_p)) * k.dxi2;
+            acc = acc + (nu_c * ((v_jm - two_v) + v_jp)) * k.dyi2;
+            acc = acc - u_here * dvdx;
+            acc = acc - v_c * dvdy;
+            acc = acc + k.gy;
+            const float dF = F_c - S.F[C].x[e - 1];
+            if (dF != 0.0f) {
+                const float kappa_ave = (k_c + S.kp[C].x[e - 1]) / 2.0f;
+                const float t = (k.neg_sigma * dF) * kappa_ave;
+                const float fy_kappa = c.fast_div_ok ? div_by_const(t, c.d_dy) : t / k.dy;
+                acc = acc + (fy_kappa * 2.0f) / (rho_c + S.rho[C].x[e - 1]);
+            }
+            ov[q] = v_c + k.dt * acc;
+        }
+    }
+    // u*: gi in [2, nx], j in [1, ny];  v*: gi in [1, nx], j in [2, ny].  Everything else is never written.
+    const bool urow = gi >= 2 && gi <= nx, vrow = gi >= 1 && gi <= nx;
+    if (jl + 3 <= ny) {
+        if (urow) *reinterpret_cast<float4*>(us + off) = make_float4(ou[0], ou[1], ou[2], ou[3]);
+        if (vrow) {
+            if (jl >= 2) *reinterpret_cast<float4*>(vs + off) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+            else { vs[off + 1] = ov[1]; vs[off + 2] = ov[2]; vs[off + 3] = ov[3]; }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = jl + q;
+            if (urow && j <= ny) us[off + q] = ou[q];
+            if (vrow && j >= 2 && j <= ny) vs[off + q] = ov[q];
+        }
+    }
+}
+
+template <bool INLINE_PROPS>
+__global__ void __launch_bounds__(32 * kMomWarps)
+k_advect4(Grid g, MomC c, const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ F,
+          const float* __restrict__ kappa, const float* __restrict__ rho, const float* __restrict__ nu,
+          float* __restrict__ us, float* __restrict__ vs, int r0, int r1, int rows_per_chunk, int nstrips) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kMomWarps + (threadIdx.x >> 5);
+    const int strip = w % nstrips, chunk = w / nstrips;
+    const int ia = r0 + chunk * rows_per_chunk;
+    if (ia > r1) return;
+    const int ib = min(r1, ia + rows_per_chunk - 1);
+    const int jl = 1 + 128 * strip + 4 * lane;
+    const bool active = jl <= g.ny + 1;
+    const int P = g.pitch;
+    const size_t col = (size_t)jl;
+    AdvState<INLINE_PROPS> S;
+    // rows ia-1 and ia enter slots 1 and 2 (OLD and MID of phase 0)
+    adv_load<INLINE_PROPS, 1>(S, c, u, v, F, kappa, rho, nu, (size_t)(ia - 1) * P + col, lane, active);
+    adv_load<INLINE_PROPS, 2>(S, c, u, v, F, kappa, rho, nu, (size_t)ia * P + col, lane, active);
+    for (int i = ia; i <= ib; i += 3) {
+        // every lane takes part in the shuffles of the loads; stores are guarded by `active` and the row range
+        adv_load<INLINE_PROPS, 0>(S, c, u, v, F, kappa, rho, nu, (size_t)min(i + 1, g.nrows - 1) * P + col, lane, active);
+        if (active) adv_row<INLINE_PROPS, 0>(S, c, us, vs, (size_t)i * P + col, g.gi0 + i, jl, g.nx, g.ny);
+        if (i + 1 > ib) break;
+        adv_load<INLINE_PROPS, 1>(S, c, u, v, F, kappa, rho, nu, (size_t)min(i + 2, g.nrows - 1) * P + col, lane, active);
+        if (active) adv_row<INLINE_PROPS, 1>(S, c, us, vs, (size_t)(i + 1) * P + col, g.gi0 + i + 1, jl, g.nx, g.ny);
+        if (i + 2 > ib) break;
+        adv_load<INLINE_PROPS, 2>(S, c, u, v, F, kappa, rho, nu, (size_t)min(i + 3, g.nrows - 1) * P + col, lane, active);
+        if (active) adv_row<INLINE_PROPS, 2>(S, c, us, vs, (size_t)(i + 2) * P + col, g.gi0 + i + 2, jl, g.nx, g.ny);
+    }
+}
+
+// ======================================================================================
+// projection, 2dvof.py:269-280: u = u* - dt/r * (p[i,j]-p[i-1,j]) * dxi, r = (rho[i,j]+rho[i-1,j])*0.5 (v alike)
+// ======================================================================================
+template <bool INLINE_PROPS>
+__global__ void __launch_bounds__(32 * kMomWarps)
+k_project4(Grid g, Consts k, const float* __restrict__ rhoF, const float* __restrict__ p, const float* __restrict__ us,
+           const float* __restrict__ vs, float* __restrict__ u, float* __restrict__ v,
+           unsigned long long* __restrict__ courant_count, int r0, int r1, int rows_per_chunk, int nstrips, int own_a,
+           int own_b) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kMomWarps + (threadIdx.x >> 5);
+    const int strip = w % nstrips, chunk = w / nstrips;
+    const int ia = r0 + chunk * rows_per_chunk;
+    if (ia > r1) return;
+    const int ib = min(r1, ia + rows_per_chunk - 1);
+    const int jl = 1 + 128 * strip + 4 * lane;
+    const bool active = jl <= g.ny;
+    const int P = g.pitch;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto ld4 = [&](const float* base, int i) { return active ? *reinterpret_cast<const float4*>(base + (size_t)i * P + jl) : zero4; };
+    auto props = [&](float4 f) {
+        return INLINE_PROPS ? make_float4(rho_of(f.x, k), rho_of(f.y, k), rho_of(f.z, k), rho_of(f.w, k)) : f;
+    };
+    float4 p_m = ld4(p, ia - 1), r_m = props(ld4(rhoF, ia - 1));
+    unsigned flags = 0;
+    float4 p_n = ld4(p, ia), f_n = ld4(rhoF, ia), us_n = ld4(us, ia), vs_n = ld4(vs, ia);
+    for (int i = ia; i <= ib; ++i) {
+        const float4 p_c = p_n, us_c = us_n, vs_c = vs_n;
+        const float4 r_c = props(f_n);
+        if (i < ib) { p_n = ld4(p, i + 1); f_n = ld4(rhoF, i + 1); us_n = ld4(us, i + 1); vs_n = ld4(vs, i + 1); }
+        const int gi = g.gi0 + i;
+        // left neighbours (column jl-1) of p and rho
+        float p_l = __shfl_up_sync(0xffffffffu, p_c.w, 1), r_l = __shfl_up_sync(0xffffffffu, r_c.w, 1);
+        if (lane == 0 && active) {
+            const size_t o = (size_t)i * P + jl - 1;
+            p_l = p[o];
+            r_l = INLINE_PROPS ? rho_of(rhoF[o], k) : rhoF[o];
+        }
+        if (!active) continue;
+        const float pc[5] = {p_l, p_c.x, p_c.y, p_c.z, p_c.w}, rc[5] = {r_l, r_c.x, r_c.y, r_c.z, r_c.w};
+        const float pm[4] = {p_m.x, p_m.y, p_m.z, p_m.w}, rm[4] = {r_m.x, r_m.y, r_m.z, r_m.w};
+        const float usv[4] = {us_c.x, us_c.y, us_c.z, us_c.w}, vsv[4] = {vs_c.x, vs_c.y, vs_c.z, vs_c.w};
+        float ou[4], ov[4];
+        const bool own = i >= own_a && i <= own_b;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float ru = (rc[q + 1] + rm[q]) * 0.5f;
+            ou[q] = usv[q] - ((k.dt / ru) * (pc[q + 1] - pm[q])) * k.dxi;
+            const float rv = (rc[q + 1] + rc[q]) * 0.5f;
+            ov[q] = vsv[q] - ((k.dt / rv) * (pc[q + 1] - pc[q])) * k.dyi;
+        }
+        const bool urow = gi >= 2 && gi <= g.nx, vrow = gi >= 1 && gi <= g.nx;
+        const size_t off = (size_t)i * P + jl;
+        if (jl + 3 <= g.ny) {
+            if (urow) {
+                *reinterpret_cast<float4*>(u + off) = make_float4(ou[0], ou[1], ou[2], ou[3]);
+                if (own) flags += (ou[0] * k.dt > k.cflx) + (ou[1] * k.dt > k.cflx) + (ou[2] * k.dt > k.cflx) + (ou[3] * k.dt > k.cflx);
+            }
+            if (vrow) {
+                if (jl >= 2) *reinterpret_cast<float4*>(v + off) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                else { v[off + 1] = ov[1]; v[off + 2] = ov[2]; v[off + 3] = ov[3]; }
+                if (own) flags += (jl >= 2 && ov[0] * k.dt > k.cfly) + (ov[1] * k.dt > k.cfly) + (ov[2] * k.dt > k.cfly) + (ov[3] * k.dt > k.cfly);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = jl + q;
+                if (urow && j <= g.ny) { u[off + q] = ou[q]; flags += own && (ou[q] * k.dt > k.cflx); }
+                if (vrow && j >= 2 && j <= g.ny) { v[off + q] = ov[q]; flags += own && (ov[q] * k.dt > k.cfly); }
+            }
+        }
+        p_m = p_c; r_m = r_c;
+    }
+    if (flags) atomicAdd(courant_count, (unsigned long long)flags);
+}
+
+}  // namespace vof
