@@ -14,6 +14,7 @@
 #include "vof2d_jacobi_tb.cuh"
 #include "vof2d_fct.cuh"
 #include "vof2d_momentum.cuh"
+#include "vof2d_kappa.cuh"
 
 using namespace vof;
 
@@ -393,11 +394,12 @@ static int run_cal_nu_rho(VofCtx* c) {
 
 static int run_kappa(VofCtx* c) {
     Span span_(c, VOF_K_KAPPA);
-    constexpr int TI = 16, TJ = 64;
     const int rows = c->in_b - c->in_a + 1;
-    dim3 grid(cdiv(c->g.ny, TJ), cdiv(rows, TI));
-    k_kappa<TI, TJ><<<grid, 256, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_KAPPA], c->in_a, c->in_b);
-    return launch_ok("k_kappa");
+    const int nstrips = cdiv(c->g.ny, kKapValid);
+    const int rpc = 64;
+    dim3 grid(cdiv(nstrips * cdiv(rows, rpc), kKapWarps));
+    k_kappa4<<<grid, 32 * kKapWarps, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_KAPPA], c->in_a, c->in_b, rpc, nstrips);
+    return launch_ok("k_kappa4");
 }
 
 constexpr int kMomRows = 64;       // rows marched by one warp of the momentum kernels
