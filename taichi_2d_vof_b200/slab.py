@@ -123,3 +123,54 @@ class SlabSolver2D:
         a = getattr(self.solver, name).to_numpy()
         H = self.solver.halo
         return a[H:a.shape[0] - H]
+
+
+class LocalSlabGroup:
+    """Several slab contexts driven by ONE process (same device or peer-mapped devices): the halo
+    exchange is vof2d_halo_push (a device-to-device copy into the neighbour's halo rows).  Used by
+    the single-GPU parity test of the decomposition; the multi-process runner is SlabSolver2D."""
+
+    def __init__(self, params_fn, nx: int, nslabs: int, halo: int | None = None, n_jacobi: int = 10, devices=None):
+        from .solver2d import VofSolver2D
+        self.parts = partition(nx, nslabs)
+        H = halo if halo is not None else max(required_halo(n_jacobi), 16)
+        devices = devices or [0] * nslabs
+        self.solvers = [VofSolver2D(params_fn(slab=self.parts[r] if nslabs > 1 else None, halo=H if nslabs > 1 else 0,
+                                              device=devices[r])) for r in range(nslabs)]
+        self.nslabs = nslabs
+
+    def exchange_halos(self):
+        S = self.solvers
+        for s in S:
+            s.synchronize()            # the producers of the rows about to be copied
+        for r in range(self.nslabs - 1):
+            lo, hi = S[r], S[r + 1]    # lo's upper side (1) faces hi's lower side (0)
+            for name in HALO_FIELDS:
+                dst_hi, _ = hi.halo_ptr(name, 0, send=False)
+                lo.halo_push(name, 1, dst_hi)
+                dst_lo, _ = lo.halo_ptr(name, 1, send=False)
+                hi.halo_push(name, 0, dst_lo)
+        for s in S:
+            s.synchronize()
+
+    def set_init_F(self, ic):
+        for s in self.solvers:
+            s.set_init_F(ic)
+
+    def step(self):
+        if self.nslabs > 1:
+            self.exchange_halos()
+        for s in self.solvers:
+            s.step()
+
+    def gather(self, name):
+        """The global (nx+2, ny+2) field assembled from the owned rows (+ the two physical ghost rows)."""
+        import numpy as np
+        rows = []
+        for r, s in enumerate(self.solvers):
+            a = getattr(s, name).to_numpy()
+            H = s.halo
+            lo = H - (1 if r == 0 else 0)
+            hi = a.shape[0] - H + (1 if r == self.nslabs - 1 else 0)
+            rows.append(a[lo:hi])
+        return np.concatenate(rows, axis=0)
