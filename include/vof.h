@@ -153,6 +153,40 @@ int vof2d_halo_ptr(VofCtx* c, int field, int side, int send, float** dev, int64_
 /* direct peer push: write my boundary rows into the neighbour's halo rows (peer-mapped memory) */
 int vof2d_halo_push(VofCtx* c, int field, int side, float* peer_halo_dst);
 
+/* =====================================================================================
+ * 3-D twin: the loop body of 3dvof.py:598-623.  Fields are the reference's (nx+2, ny+2, nz+2) fp32
+ * arrays, index [i, j, k], k contiguous (3dvof.py:70-117); on the device element (i, j, k) is
+ * dev[i * pitch_j + j * pitch_k + k].  Same conventions as above.  3dvof.py never computes the
+ * curvature (line 607 is commented out) and only -ic 1 sets F (126-138); both are reproduced.
+ * ===================================================================================== */
+typedef struct Vof3Ctx Vof3Ctx;
+size_t vof3d_arena_bytes(const VofParams* p);
+int vof3d_create(const VofParams* p, Vof3Ctx** out);       /* ti.init + fields, 3dvof.py:10, 70-117   */
+int vof3d_destroy(Vof3Ctx* c);
+int vof3d_set_stream(Vof3Ctx* c, void* cuda_stream);
+int vof3d_synchronize(Vof3Ctx* c);
+int vof3d_get_params(const Vof3Ctx* c, VofParams* out);
+int vof3d_set_init_F(Vof3Ctx* c, int ic);                  /* 3dvof.py:126-138                         */
+int vof3d_set_BC(Vof3Ctx* c);                              /* 3dvof.py:141-190                         */
+int vof3d_cal_nu_rho(Vof3Ctx* c);                          /* 3dvof.py:199-204                         */
+int vof3d_advect_upwind(Vof3Ctx* c);                       /* 3dvof.py:207-258                         */
+int vof3d_solve_p_jacobi(Vof3Ctx* c, int nsweeps);         /* 3dvof.py:261-283                         */
+int vof3d_update_uv(Vof3Ctx* c);                           /* 3dvof.py:286-302                         */
+int vof3d_fct_x_sweep(Vof3Ctx* c);                         /* 3dvof.py:366-427                         */
+int vof3d_fct_y_sweep(Vof3Ctx* c);                         /* 3dvof.py:430-492                         */
+int vof3d_fct_z_sweep(Vof3Ctx* c);                         /* 3dvof.py:495-541                         */
+int vof3d_solve_VOF_rudman(Vof3Ctx* c, int istep);         /* 3dvof.py:351-363                         */
+int vof3d_post_process_f(Vof3Ctx* c);                      /* 3dvof.py:544-547                         */
+int vof3d_step(Vof3Ctx* c, int istep, unsigned flags);     /* 3dvof.py:606-623                         */
+int vof3d_run(Vof3Ctx* c, int istep0, int nsteps, unsigned flags);
+int vof3d_field_ptr(Vof3Ctx* c, int field, float** dev, int64_t* pitch_k, int64_t* pitch_j, int64_t* planes);
+int vof3d_field_get(Vof3Ctx* c, int field, float* host_dst);   /* F.to_numpy(), 3dvof.py:627         */
+int vof3d_field_set(Vof3Ctx* c, int field, const float* host_src);
+int vof3d_diagnostics(Vof3Ctx* c, double* mass, float* max_cfl, int64_t* courant_count);
+int64_t vof3d_launch_count(const Vof3Ctx* c);
+int vof3d_halo_ptr(Vof3Ctx* c, int field, int side, int send, float** dev, int64_t* count);
+int vof3d_halo_push(Vof3Ctx* c, int field, int side, float* peer_halo_dst);
+
 #ifdef __cplusplus
 }
 #endif

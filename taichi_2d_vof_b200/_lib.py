@@ -96,6 +96,33 @@ SIGNATURES = {
     "vof2d_halo_rows": (C.c_int, [_ctx, _P(C.c_int), _P(C.c_int64)]),
     "vof2d_halo_ptr": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _P(C.c_void_p), _P(C.c_int64)]),
     "vof2d_halo_push": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p]),
+    # ---- 3-D
+    "vof3d_arena_bytes": (C.c_size_t, [_P(VofParams)]),
+    "vof3d_create": (C.c_int, [_P(VofParams), _P(_ctx)]),
+    "vof3d_destroy": (C.c_int, [_ctx]),
+    "vof3d_set_stream": (C.c_int, [_ctx, C.c_void_p]),
+    "vof3d_synchronize": (C.c_int, [_ctx]),
+    "vof3d_get_params": (C.c_int, [_ctx, _P(VofParams)]),
+    "vof3d_set_init_F": (C.c_int, [_ctx, C.c_int]),
+    "vof3d_set_BC": (C.c_int, [_ctx]),
+    "vof3d_cal_nu_rho": (C.c_int, [_ctx]),
+    "vof3d_advect_upwind": (C.c_int, [_ctx]),
+    "vof3d_solve_p_jacobi": (C.c_int, [_ctx, C.c_int]),
+    "vof3d_update_uv": (C.c_int, [_ctx]),
+    "vof3d_fct_x_sweep": (C.c_int, [_ctx]),
+    "vof3d_fct_y_sweep": (C.c_int, [_ctx]),
+    "vof3d_fct_z_sweep": (C.c_int, [_ctx]),
+    "vof3d_solve_VOF_rudman": (C.c_int, [_ctx, C.c_int]),
+    "vof3d_post_process_f": (C.c_int, [_ctx]),
+    "vof3d_step": (C.c_int, [_ctx, C.c_int, C.c_uint]),
+    "vof3d_run": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_uint]),
+    "vof3d_field_ptr": (C.c_int, [_ctx, C.c_int, _P(C.c_void_p), _P(C.c_int64), _P(C.c_int64), _P(C.c_int64)]),
+    "vof3d_field_get": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
+    "vof3d_field_set": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
+    "vof3d_diagnostics": (C.c_int, [_ctx, _P(C.c_double), _P(C.c_float), _P(C.c_int64)]),
+    "vof3d_launch_count": (C.c_int64, [_ctx]),
+    "vof3d_halo_ptr": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _P(C.c_void_p), _P(C.c_int64)]),
+    "vof3d_halo_push": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p]),
 }
 
 

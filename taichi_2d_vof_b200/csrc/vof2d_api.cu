@@ -1,15 +1,6 @@
 // libvof C ABI (include/vof.h) -- 2-D context, launches, field access, diagnostics.
 // Host code only decides ranges and launch shapes; all arithmetic is in vof2d_kernels.cuh.
-#include <cuda_runtime.h>
-
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <new>
-#include <vector>
-
+#include "vof_host_common.h"
 #include "vof2d_kernels.cuh"
 #include "vof2d_jacobi_tb.cuh"
 #include "vof2d_fct.cuh"
@@ -18,27 +9,13 @@
 
 using namespace vof;
 
-// ------------------------------------------------------------------------------------
-// errors
-// ------------------------------------------------------------------------------------
-static thread_local char g_err[512] = "";
-static int fail(int code, const char* fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-    return code;
-}
-#define CU(call)                                                                             \
-    do {                                                                                     \
-        cudaError_t e_ = (call);                                                             \
-        if (e_ != cudaSuccess)                                                               \
-            return fail((int)e_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-#define CHECK_CTX(c) \
-    do { if (!(c)) return fail(VOF_EINVAL, "null context"); } while (0)
+using vofhost::cdiv;
+using vofhost::fail;
+using vofhost::launch_ok;
+using vofhost::make_const_div;
+using vofhost::node_coords;
 
-extern "C" const char* vof_last_error(void) { return g_err; }
+extern "C" const char* vof_last_error(void) { return vofhost::g_err; }
 extern "C" int vof_abi_version(void) { return VOF_ABI_VERSION; }
 
 extern "C" void vof_default_params(VofParams* p) {
@@ -104,14 +81,6 @@ struct VofCtx {
     float* p_alt() { return buf[p_cur ? BUF_P0 : BUF_P1]; }
 };
 
-static ConstDiv make_const_div(float b) {
-    ConstDiv d;
-    d.b = b; d.bd = (double)b;
-    d.rd = 1.0 / d.bd;            // RN64(1/b)
-    d.r = (float)d.rd;            // RN32(1/b) up to double rounding; the exhaustive device check is the proof
-    return d;
-}
-
 static size_t field_stride_bytes(int nrows, int pitch) {
     size_t b = (size_t)nrows * pitch * sizeof(float);
     return (b + 255) / 256 * 256;
@@ -149,15 +118,6 @@ extern "C" size_t vof2d_arena_bytes(const VofParams* p) {
     if (resolve(p, &P, &g, &lo, &hi, &H) != VOF_OK) return 0;
     size_t xy = ((size_t)(P.nx + 3 + P.ny + 3) * sizeof(float) + 255) / 256 * 256;
     return field_stride_bytes(g.nrows, g.pitch) * BUF_COUNT + xy + 256;
-}
-
-static void node_coords(std::vector<float>& x, int n, double L) {
-    // np.hstack((0.0, np.linspace(0, L, n + 1), L)).astype(float32), 2dvof.py:43-46
-    x.assign((size_t)n + 3, 0.0f);
-    const double step = L / n;
-    for (int k = 0; k <= n; ++k) x[(size_t)k + 1] = (float)(k == n ? L : k * step);
-    x[0] = 0.0f;
-    x[(size_t)n + 2] = (float)L;
 }
 
 static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, VofCtx** out) {
@@ -346,14 +306,6 @@ extern "C" int vof2d_get_params(const VofCtx* c, VofParams* out) {
 // ------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------
-static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
-static int launch_ok(const char* what) {
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail((int)e, "launch of %s failed: %s", what, cudaGetErrorString(e));
-    return VOF_OK;
-}
-#define TRY(x) do { int rc_ = (x); if (rc_ != VOF_OK) return rc_; } while (0)
-
 // RAII span: counts the launch and, when profiling, brackets it with events on the ctx stream
 struct Span {
     VofCtx* c; int kind; cudaEvent_t b;

@@ -64,7 +64,7 @@ struct JacTB {
 };
 
 // exhaustive check of div_by_const against IEEE division: every fp32 bit pattern
-__global__ void k_check_div_by_const(ConstDiv d, unsigned long long* mismatches) {
+static __global__ void k_check_div_by_const(ConstDiv d, unsigned long long* mismatches) {
     const unsigned long long n = 1ull << 32;
     unsigned long long bad = 0;
     for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n;
@@ -93,7 +93,7 @@ struct JacEdge {
 
 // rows that touch an i-wall, ghost rows and rows outside the field: the reference's expression with
 // every coefficient selected, IEEE division, pass-through for non-interior cells.  Out of line: rare.
-__device__ __noinline__ float4 jac_general_row(float4 up, float4 md, float4 dn, float left, float right, float4 b,
+static __device__ __noinline__ float4 jac_general_row(float4 up, float4 md, float4 dn, float left, float right, float4 b,
                                                int gi, int jl, int nx, int ny, JacTB jc) {
     const bool rowin = gi >= 1 && gi <= nx;
     const float ae = (gi != nx) ? jc.cx : 0.0f;
@@ -273,7 +273,7 @@ k_jacobi_tb(Grid g, JacTB jc, JacSched sc, const float* __restrict__ p, float* _
 
 // ghost cells of the field pass through a sweep unchanged; the pipeline above only stores columns of
 // output lanes, so the API entry (not the fused step, where set_BC rewrites them) copies the frame.
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_copy_frame(Grid g, const float* __restrict__ src, float* __restrict__ dst, int row_a, int row_b, int copy_lo_row,
              int copy_hi_row) {
     const int t = blockIdx.x * 128 + threadIdx.x;
