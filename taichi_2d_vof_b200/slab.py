@@ -130,14 +130,17 @@ class LocalSlabGroup:
     exchange is vof2d_halo_push (a device-to-device copy into the neighbour's halo rows).  Used by
     the single-GPU parity test of the decomposition; the multi-process runner is SlabSolver2D."""
 
-    def __init__(self, params_fn, nx: int, nslabs: int, halo: int | None = None, n_jacobi: int = 10, devices=None):
-        from .solver2d import VofSolver2D
+    def __init__(self, params_fn, nx: int, nslabs: int, halo: int | None = None, n_jacobi: int = 10, devices=None,
+                 solver_cls=None, halo_fields=HALO_FIELDS):
+        if solver_cls is None:
+            from .solver2d import VofSolver2D as solver_cls
         self.parts = partition(nx, nslabs)
         H = halo if halo is not None else max(required_halo(n_jacobi), 16)
         devices = devices or [0] * nslabs
-        self.solvers = [VofSolver2D(params_fn(slab=self.parts[r] if nslabs > 1 else None, halo=H if nslabs > 1 else 0,
-                                              device=devices[r])) for r in range(nslabs)]
+        self.solvers = [solver_cls(params_fn(slab=self.parts[r] if nslabs > 1 else None, halo=H if nslabs > 1 else 0,
+                                             device=devices[r])) for r in range(nslabs)]
         self.nslabs = nslabs
+        self.halo_fields = halo_fields
 
     def exchange_halos(self):
         S = self.solvers
@@ -145,7 +148,7 @@ class LocalSlabGroup:
             s.synchronize()            # the producers of the rows about to be copied
         for r in range(self.nslabs - 1):
             lo, hi = S[r], S[r + 1]    # lo's upper side (1) faces hi's lower side (0)
-            for name in HALO_FIELDS:
+            for name in self.halo_fields:
                 dst_hi, _ = hi.halo_ptr(name, 0, send=False)
                 lo.halo_push(name, 1, dst_hi)
                 dst_lo, _ = lo.halo_ptr(name, 1, send=False)

@@ -141,3 +141,34 @@ def test_roundoff_perturbation_stays_within_north_star_tolerance():
     a.run(99); b.run(99)
     for k in ("u", "v", "p", "F"):
         assert rel_linf(getattr(b, k), getattr(a, k)) < 1e-3, k
+
+
+def test_3d_numpy_and_c_oracles_identical():
+    from oracle.c_oracle import Vof3DCOracle
+    from oracle.vof3d_oracle import Vof3DOracle, Vof3DParams
+    P = Vof3DParams(nx=14, ny=19, nz=11, Lx=0.007, Ly=0.0095, Lz=0.0055)
+    a, b = Vof3DOracle(P), Vof3DCOracle(P)
+    a.set_init_F(1); b.set_init_F(1)
+    for _ in range(9):      # three full rotations of the sweep order
+        a.step(); b.step()
+    for k in a.FIELDS:
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_3d_known_answers():
+    """From rest: v* = dt*gy in the bulk, u* = w* = 0; only -ic 1 writes F; sweep order rotates with istep % 3."""
+    from oracle.vof3d_oracle import Vof3DOracle, Vof3DParams
+    o = Vof3DOracle(Vof3DParams.scaled(20))
+    o.set_init_F(2)
+    assert not o.F.any()
+    o.set_init_F(1)
+    assert o.F[1, 1, 1] == 1 and o.F[15, 15, 15] == 0
+    o.istep += 1
+    o.cal_nu_rho(); o.advect_upwind()
+    assert np.all(o.v_star[1:21, 2:21, 1:21][12:, 14:, 12:] == np.float32(4e-6) * np.float32(-5))
+    assert not o.u_star[:, :, :][12:, 14:, 12:].any() and not o.w_star[12:, 14:, 12:].any()
+    calls = []
+    o._fct_sweep = lambda ax: calls.append(ax)
+    for istep in (1, 2, 3):
+        o.istep = istep; o.solve_VOF_rudman()
+    assert calls == [1, 2, 0, 2, 0, 1, 0, 1, 2]
