@@ -49,7 +49,10 @@ timeit("solve_p_jacobi(10) TB 5+5 (+rhs)", lambda: s.solve_p_jacobi(10), 12, 10)
 timeit("solve_p_jacobi(5) TB (+rhs)", lambda: s.solve_p_jacobi(5), 12, 5)
 timeit("update_uv", s.update_uv, 24)
 fill()
-timeit("fct_x_sweep", s.fct_x_sweep, 12)
+s.set_option(_lib.VOF_OPT_FCT_X_COLS, 4)
+timeit("fct_x_sweep (4 cols/lane)", s.fct_x_sweep, 12)
+s.set_option(_lib.VOF_OPT_FCT_X_COLS, 2)
+timeit("fct_x_sweep (2 cols/lane)", s.fct_x_sweep, 12)
 timeit("fct_y_sweep", s.fct_y_sweep, 12)
 timeit("set_BC", s.set_BC, 0)
 timeit("step (fused)", s.step, 216)

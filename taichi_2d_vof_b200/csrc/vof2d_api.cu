@@ -69,6 +69,7 @@ struct VofCtx {
     JacTB jac;                 // constants of the temporally blocked Jacobi
     int jac_resident_warps[6]; // warps of k_jacobi_tb<T> resident on the whole GPU, by T
     int opt_jacobi_tb;         // 1: temporal blocking (default), 0: one launch per sweep
+    int opt_fct_x_cols;        // columns per lane of the x-sweep (2 or 4)
     int sm_count;
     // launch accounting + optional per-kernel-kind CUDA-event timing (vof2d_profile)
     long long launches;
@@ -199,6 +200,7 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     }
     c->mom.k = k; c->mom.d_dx = make_const_div(k.dx); c->mom.d_dy = make_const_div(k.dy); c->mom.fast_div_ok = 0;
     c->opt_jacobi_tb = 1;
+    c->opt_fct_x_cols = 2;
     c->sm_count = prop.multiProcessorCount;
     c->all_a = std::max(0, -g.gi0);
     c->all_b = std::min(g.nrows - 1, P.nx + 1 - g.gi0);
@@ -472,11 +474,19 @@ static int run_project(VofCtx* c, bool inline_props) {
 static int run_fct_x(VofCtx* c, bool post) {
     Span span_(c, VOF_K_FCT_X);
     const int rows = c->in_b - c->in_a + 1;
-    const int nstrips = cdiv(c->g.ny + 1, 128);
+    const int nc = c->opt_fct_x_cols;
+    const int nstrips = cdiv(c->g.ny + 1, 32 * nc);
     const int nwarps = nstrips * cdiv(rows, kFctRows);
     dim3 grid(cdiv(nwarps, kFctXWarps));
-    if (post) k_fct_x4<true><<<grid, 32 * kFctXWarps, 0, c->stream>>>(c->g, c->fctx, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, kFctRows, nstrips);
-    else k_fct_x4<false><<<grid, 32 * kFctXWarps, 0, c->stream>>>(c->g, c->fctx, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, kFctRows, nstrips);
+#define FXA c->g, c->fctx, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, kFctRows, nstrips
+    if (nc == 2) {
+        if (post) k_fct_x4<true, 2><<<grid, 32 * kFctXWarps, 0, c->stream>>>(FXA);
+        else k_fct_x4<false, 2><<<grid, 32 * kFctXWarps, 0, c->stream>>>(FXA);
+    } else {
+        if (post) k_fct_x4<true, 4><<<grid, 32 * kFctXWarps, 0, c->stream>>>(FXA);
+        else k_fct_x4<false, 4><<<grid, 32 * kFctXWarps, 0, c->stream>>>(FXA);
+    }
+#undef FXA
     c->F_cur ^= 1;
     return launch_ok("k_fct_x4");
 }
@@ -803,6 +813,7 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
     CHECK_CTX(c);
     switch (option) {
         case VOF_OPT_JACOBI_TB: c->opt_jacobi_tb = value != 0; break;
+        case VOF_OPT_FCT_X_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "fct_x columns per lane must be 2 or 4"); c->opt_fct_x_cols = value; break;
         default: return fail(VOF_EINVAL, "unknown option %d", option);
     }
     for (int a = 0; a < 2; ++a)

@@ -95,7 +95,20 @@ __device__ __forceinline__ float fct_update2(float td_c, float a_c, float c_c, f
 // ======================================================================================
 constexpr int kFctXWarps = 4;
 
-template <bool POST>
+// NC consecutive floats as one vector load / store (NC = 2 or 4)
+template <int NC> struct VecN;
+template <> struct VecN<4> {
+    static __device__ __forceinline__ void ld(const float* p, float (&x)[4]) { const float4 v = *reinterpret_cast<const float4*>(p); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+    static __device__ __forceinline__ void st(float* p, const float (&x)[4]) { *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]); }
+};
+template <> struct VecN<2> {
+    static __device__ __forceinline__ void ld(const float* p, float (&x)[2]) { const float2 v = *reinterpret_cast<const float2*>(p); x[0] = v.x; x[1] = v.y; }
+    static __device__ __forceinline__ void st(float* p, const float (&x)[2]) { *reinterpret_cast<float2*>(p) = make_float2(x[0], x[1]); }
+};
+
+// NC columns per lane: 4 = fewest instructions per cell, 2 = half the registers (twice the resident warps);
+// the sweep is latency bound, so the narrower variant wins on B200 (profiles/)
+template <bool POST, int NC>
 __global__ void __launch_bounds__(32 * kFctXWarps)
 k_fct_x4(Grid g, FctC c, const float* __restrict__ Fin, const float* __restrict__ u, float* __restrict__ Fout,
          int r0, int r1, int rows_per_chunk, int nstrips) {
@@ -105,48 +118,44 @@ k_fct_x4(Grid g, FctC c, const float* __restrict__ Fin, const float* __restrict_
     const int ia = r0 + chunk * rows_per_chunk;
     if (ia > r1) return;
     const int ib = min(r1, ia + rows_per_chunk - 1);
-    const int jl = 1 + 128 * strip + 4 * lane;
+    const int jl = 1 + 32 * NC * strip + NC * lane;
     if (jl > g.ny + 1) return;
     const int P = g.pitch, last = g.nrows - 1;
     const float* Fc = Fin + jl;
     const float* uc = u + jl;
     float* Fo = Fout + jl;
-    auto ld4 = [&](const float* base, int i) { return *reinterpret_cast<const float4*>(base + (size_t)min(max(i, 0), last) * P); };
+    auto ldv = [&](const float* base, int i, float (&x)[NC]) { VecN<NC>::ld(base + (size_t)min(max(i, 0), last) * P, x); };
     const bool lo_wall = g.gi0 + ia == 1, hi_wall = g.gi0 + ib == g.nx;
     // ghost rows / ghost column 0 pass through (the sweep never writes them; out-of-place needs the copy)
-    if (lo_wall) *reinterpret_cast<float4*>(Fo + (size_t)(ia - 1) * P) = ld4(Fc, ia - 1);
-    if (hi_wall) *reinterpret_cast<float4*>(Fo + (size_t)(ib + 1) * P) = ld4(Fc, ib + 1);
+    if (lo_wall) { float t[NC]; ldv(Fc, ia - 1, t); VecN<NC>::st(Fo + (size_t)(ia - 1) * P, t); }
+    if (hi_wall) { float t[NC]; ldv(Fc, ib + 1, t); VecN<NC>::st(Fo + (size_t)(ib + 1) * P, t); }
     if (strip == 0 && lane == 0) {
         for (int i = ia - (lo_wall ? 1 : 0); i <= ib + (hi_wall ? 1 : 0); ++i) Fout[(size_t)i * P] = Fin[(size_t)i * P];
     }
-    bool colin[4];
+    bool colin[NC];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) colin[k] = jl + k <= g.ny;
+    for (int k = 0; k < NC; ++k) colin[k] = jl + k <= g.ny;
 
-    float F1[4], u1[4], lo1[4], a1[4], a2[4], a3[4], td1[4], td2[4], td3[4], dv1[4], dv2[4], dv3[4], rp2[4], rm2[4], c2[4];
-    float Fk[4], uk[4];
-    {
-        const float4 f = ld4(Fc, ia - 3), fk = ld4(Fc, ia - 2), uu = ld4(uc, ia - 2);
-        F1[0] = f.x; F1[1] = f.y; F1[2] = f.z; F1[3] = f.w;
-        Fk[0] = fk.x; Fk[1] = fk.y; Fk[2] = fk.z; Fk[3] = fk.w;
-        uk[0] = uu.x; uk[1] = uu.y; uk[2] = uu.z; uk[3] = uu.w;
-    }
+    float F1[NC], u1[NC], lo1[NC], a1[NC], a2[NC], a3[NC], td1[NC], td2[NC], td3[NC], dv1[NC], dv2[NC], dv3[NC], rp2[NC], rm2[NC], c2[NC];
+    float Fk[NC], uk[NC];
+    ldv(Fc, ia - 3, F1); ldv(Fc, ia - 2, Fk); ldv(uc, ia - 2, uk);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < NC; ++k) {
         u1[k] = 0.f; lo1[k] = 0.f; a1[k] = a2[k] = a3[k] = 0.f; td1[k] = td2[k] = td3[k] = 0.f;
         dv1[k] = dv2[k] = dv3[k] = 1.f; rp2[k] = rm2[k] = 0.f; c2[k] = 0.f;
     }
     for (int k = ia - 2; k <= ib + 3; ++k) {
-        const float4 Fn = ld4(Fc, k + 1), un = ld4(uc, k + 1);          // prefetch the next row
+        float Fn[NC], un[NC];
+        ldv(Fc, k + 1, Fn); ldv(uc, k + 1, un);                         // prefetch the next row
         const int gk = g.gi0 + k;
         const bool in1 = gk - 1 >= 1 && gk - 1 <= g.nx;                 // cell k-1 interior
         const bool in2 = gk - 2 >= 1 && gk - 2 <= g.nx;                 // cell k-2 interior
         const bool face2 = gk - 2 >= 2 && gk - 2 <= g.nx + 1;           // face k-2 has a limiter (cx[1] is never written)
         const int io = k - 3;
         const bool store = io >= ia && io <= ib;                        // rows ia..ib are interior by construction
-        float out[4];
+        float out[NC];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < NC; ++q) {
             float lo0, a0;
             fct_face(uk[q], F1[q], Fk[q], c, lo0, a0);                                   // face k
             const float dv_n = c.dxdy - c.dtd * (uk[q] - u1[q]);                         // cell k-1
@@ -162,16 +171,16 @@ k_fct_x4(Grid g, FctC c, const float* __restrict__ Fin, const float* __restrict_
             F1[q] = Fk[q]; u1[q] = uk[q];
         }
         if (store) {
-            if (colin[3]) {
-                *reinterpret_cast<float4*>(Fo + (size_t)io * P) = make_float4(out[0], out[1], out[2], out[3]);
-            } else {                             // pass-through for columns past ny (ghost ny+1, padding)
-                const float4 old = ld4(Fc, io);
-                *reinterpret_cast<float4*>(Fo + (size_t)io * P) =
-                    make_float4(colin[0] ? out[0] : old.x, colin[1] ? out[1] : old.y, colin[2] ? out[2] : old.z, old.w);
+            if (!colin[NC - 1]) {                 // pass-through for columns past ny (ghost ny+1, padding)
+                float old[NC];
+                ldv(Fc, io, old);
+#pragma unroll
+                for (int q = 0; q < NC; ++q) out[q] = colin[q] ? out[q] : old[q];
             }
+            VecN<NC>::st(Fo + (size_t)io * P, out);
         }
-        Fk[0] = Fn.x; Fk[1] = Fn.y; Fk[2] = Fn.z; Fk[3] = Fn.w;
-        uk[0] = un.x; uk[1] = un.y; uk[2] = un.z; uk[3] = un.w;
+#pragma unroll
+        for (int q = 0; q < NC; ++q) { Fk[q] = Fn[q]; uk[q] = un[q]; }
     }
 }
 
