@@ -40,7 +40,10 @@ def timeit(name, fn, cells_bytes, updates=1):
 
 fill()
 timeit("get_normal_young", s.get_normal_young, 8)
-timeit("advect_upwind", s.advect_upwind, 24)
+s.set_option(_lib.VOF_OPT_ADVECT_COLS, 4)
+timeit("advect_upwind (4 cols/lane)", s.advect_upwind, 24)
+s.set_option(_lib.VOF_OPT_ADVECT_COLS, 2)
+timeit("advect_upwind (2 cols/lane)", s.advect_upwind, 24)
 timeit("solve_p_jacobi(1)", lambda: s.solve_p_jacobi(1), 20)
 s.set_option(_lib.VOF_OPT_JACOBI_TB, 0)
 timeit("solve_p_jacobi(10) no TB (+rhs)", lambda: s.solve_p_jacobi(10), 12, 10)

@@ -20,6 +20,7 @@ FIELD_IDS = {"F": VOF_F, "u": VOF_U, "v": VOF_V, "p": VOF_P, "rho": VOF_RHO, "nu
 KERNEL_KINDS = ("props", "kappa", "advect", "bc", "rhs", "jacobi", "project", "fct_x", "fct_y", "post", "halo")
 VOF_OPT_JACOBI_TB = 0
 VOF_OPT_FCT_X_COLS = 1
+VOF_OPT_ADVECT_COLS = 2
 VOF_STEP_MATERIALIZE_PROPS = 1
 VOF_STEP_NO_FUSION = 2
 VOF_SLAB_MIN_HALO = 13

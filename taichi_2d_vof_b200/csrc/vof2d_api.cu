@@ -70,6 +70,7 @@ struct VofCtx {
     int jac_resident_warps[6]; // warps of k_jacobi_tb<T> resident on the whole GPU, by T
     int opt_jacobi_tb;         // 1: temporal blocking (default), 0: one launch per sweep
     int opt_fct_x_cols;        // columns per lane of the x-sweep (2 or 4)
+    int opt_advect_cols;       // columns per lane of the momentum predictor (2 or 4)
     int sm_count;
     // launch accounting + optional per-kernel-kind CUDA-event timing (vof2d_profile)
     long long launches;
@@ -201,6 +202,7 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     c->mom.k = k; c->mom.d_dx = make_const_div(k.dx); c->mom.d_dy = make_const_div(k.dy); c->mom.fast_div_ok = 0;
     c->opt_jacobi_tb = 1;
     c->opt_fct_x_cols = 2;
+    c->opt_advect_cols = 2;
     c->sm_count = prop.multiProcessorCount;
     c->all_a = std::max(0, -g.gi0);
     c->all_b = std::min(g.nrows - 1, P.nx + 1 - g.gi0);
@@ -362,14 +364,18 @@ static int run_advect(VofCtx* c, bool inline_props) {
     Span span_(c, VOF_K_ADVECT);
     const int a = std::max(c->in_a, 1), b = std::min(c->in_b, c->g.nrows - 2);
     const int rows = b - a + 1;
-    const int nstrips = cdiv(c->g.ny, 128);
+    const int nc = c->opt_advect_cols;
+    const int nstrips = cdiv(c->g.ny, 32 * nc);
     dim3 grid(cdiv(nstrips * cdiv(rows, kMomRows), kMomWarps));
-    if (inline_props)
-        k_advect4<true><<<grid, 32 * kMomWarps, 0, c->stream>>>(c->g, c->mom, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->buf[BUF_KAPPA], nullptr,
-                                                              nullptr, c->buf[BUF_US], c->buf[BUF_VS], a, b, kMomRows, nstrips);
-    else
-        k_advect4<false><<<grid, 32 * kMomWarps, 0, c->stream>>>(c->g, c->mom, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->buf[BUF_KAPPA],
-                                                               c->buf[BUF_RHO], c->buf[BUF_NU], c->buf[BUF_US], c->buf[BUF_VS], a, b, kMomRows, nstrips);
+#define ADA c->g, c->mom, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->buf[BUF_KAPPA], c->buf[BUF_RHO], c->buf[BUF_NU], c->buf[BUF_US], c->buf[BUF_VS], a, b, kMomRows, nstrips
+    if (nc == 2) {
+        if (inline_props) k_advect4<true, 2><<<grid, 32 * kMomWarps, 0, c->stream>>>(ADA);
+        else k_advect4<false, 2><<<grid, 32 * kMomWarps, 0, c->stream>>>(ADA);
+    } else {
+        if (inline_props) k_advect4<true, 4><<<grid, 32 * kMomWarps, 0, c->stream>>>(ADA);
+        else k_advect4<false, 4><<<grid, 32 * kMomWarps, 0, c->stream>>>(ADA);
+    }
+#undef ADA
     return launch_ok("k_advect4");
 }
 
@@ -813,6 +819,7 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
     CHECK_CTX(c);
     switch (option) {
         case VOF_OPT_JACOBI_TB: c->opt_jacobi_tb = value != 0; break;
+        case VOF_OPT_ADVECT_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "advect columns per lane must be 2 or 4"); c->opt_advect_cols = value; break;
         case VOF_OPT_FCT_X_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "fct_x columns per lane must be 2 or 4"); c->opt_fct_x_cols = value; break;
         default: return fail(VOF_EINVAL, "unknown option %d", option);
     }

@@ -7,6 +7,7 @@
 // Arithmetic is the reference's, term for term; the only short-cut is exact: the CSF term is skipped
 // where F has no jump across the face (it is then +-0, and x + (+-0) = x).
 #pragma once
+#include "vof2d_fct.cuh"
 #include "vof2d_jacobi_tb.cuh"
 #include "vof_common.cuh"
 
@@ -20,66 +21,68 @@ struct MomC {
     int fast_div_ok;
 };
 
-// x[-1..4] of one row: [0] = left neighbour (column jl-1), [1..4] = own columns, [5] = right neighbour (jl+4)
-struct Row6 { float x[6]; };
+// one row of a field as seen by a lane: [0] = left neighbour (column jl-1), [1..NC] = own columns,
+// [NC+1] = right neighbour (jl+NC)
+template <int NC> struct RowN { float x[NC + 2]; };
 
-__device__ __forceinline__ void load_row6(Row6& r, const float* __restrict__ base, size_t off, int lane, bool active,
-                                          bool need_left, bool need_right) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) v = *reinterpret_cast<const float4*>(base + off);
-    r.x[1] = v.x; r.x[2] = v.y; r.x[3] = v.z; r.x[4] = v.w;
+template <int NC>
+__device__ __forceinline__ void load_row(RowN<NC>& r, const float* __restrict__ base, size_t off, int lane, bool active,
+                                         bool need_left, bool need_right) {
+    float v[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) v[q] = 0.0f;
+    if (active) VecN<NC>::ld(base + off, v);
+#pragma unroll
+    for (int q = 0; q < NC; ++q) r.x[q + 1] = v[q];
     if (need_left) {
-        r.x[0] = __shfl_up_sync(0xffffffffu, v.w, 1);
+        r.x[0] = __shfl_up_sync(0xffffffffu, v[NC - 1], 1);
         if (lane == 0 && active) r.x[0] = base[off - 1];
     }
     if (need_right) {
-        r.x[5] = __shfl_down_sync(0xffffffffu, v.x, 1);
-        if (lane == 31 && active) r.x[5] = base[off + 4];
+        r.x[NC + 1] = __shfl_down_sync(0xffffffffu, v[0], 1);
+        if (lane == 31 && active) r.x[NC + 1] = base[off + NC];
     }
 }
 
-template <bool INLINE_PROPS>
+template <bool INLINE_PROPS, int NC>
 struct AdvState {
-    Row6 u[3], v[3];       // ring over rows i-1, i, i+1
-    Row6 F[3], kp[3];      // F and kappa: own columns + left neighbour
-    Row6 rho[3];           // rho: own columns + left neighbour
-    float nu[3][4];
+    RowN<NC> u[3], v[3];       // ring over rows i-1, i, i+1
+    RowN<NC> F[3], kp[3];      // F and kappa: own columns + left neighbour
+    float nu[3][NC];           // rho is only needed by the CSF term, i.e. at the interface: fetched / recomputed there
 };
 
-template <bool INLINE_PROPS, int PH>
-__device__ __forceinline__ void adv_load(AdvState<INLINE_PROPS>& S, const MomC& c, const float* __restrict__ u,
+template <bool INLINE_PROPS, int NC, int PH>
+__device__ __forceinline__ void adv_load(AdvState<INLINE_PROPS, NC>& S, const MomC& c, const float* __restrict__ u,
                                          const float* __restrict__ v, const float* __restrict__ F,
                                          const float* __restrict__ kappa, const float* __restrict__ rho,
                                          const float* __restrict__ nu, size_t off, int lane, bool active) {
-    load_row6(S.u[PH], u, off, lane, active, true, true);
-    load_row6(S.v[PH], v, off, lane, active, true, true);
-    load_row6(S.F[PH], F, off, lane, active, true, false);
-    load_row6(S.kp[PH], kappa, off, lane, active, true, false);
+    load_row<NC>(S.u[PH], u, off, lane, active, true, true);
+    load_row<NC>(S.v[PH], v, off, lane, active, true, true);
+    load_row<NC>(S.F[PH], F, off, lane, active, true, false);
+    load_row<NC>(S.kp[PH], kappa, off, lane, active, true, false);
     if (INLINE_PROPS) {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) S.rho[PH].x[q] = rho_of(S.F[PH].x[q], c.k);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) S.nu[PH][q] = nu_of(S.F[PH].x[q + 1], c.k);
+        for (int q = 0; q < NC; ++q) S.nu[PH][q] = nu_of(S.F[PH].x[q + 1], c.k);
     } else {
-        load_row6(S.rho[PH], rho, off, lane, active, true, false);
-        float4 n = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) n = *reinterpret_cast<const float4*>(nu + off);
-        S.nu[PH][0] = n.x; S.nu[PH][1] = n.y; S.nu[PH][2] = n.z; S.nu[PH][3] = n.w;
+#pragma unroll
+        for (int q = 0; q < NC; ++q) S.nu[PH][q] = 0.0f;
+        if (active) VecN<NC>::ld(nu + off, S.nu[PH]);
     }
 }
 
 // row i = slot MID; writes u*(i, .) and v*(i, .)
-template <bool INLINE_PROPS, int PH>
-__device__ __forceinline__ void adv_row(const AdvState<INLINE_PROPS>& S, const MomC& c, float* __restrict__ us,
-                                        float* __restrict__ vs, size_t off, int gi, int jl, int nx, int ny) {
+template <bool INLINE_PROPS, int NC, int PH>
+__device__ __forceinline__ void adv_row(const AdvState<INLINE_PROPS, NC>& S, const MomC& c, const float* __restrict__ rho,
+                                        int P, float* __restrict__ us, float* __restrict__ vs, size_t off, int gi, int jl,
+                                        int nx, int ny) {
     constexpr int P1 = PH, C = (PH + 2) % 3, M = (PH + 1) % 3;   // rows i+1, i, i-1
     const Consts& k = c.k;
-    float ou[4], ov[4];
+    float ou[NC], ov[NC];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int e = q + 1;                      // index into Row6
+    for (int q = 0; q < NC; ++q) {
+        const int e = q + 1;                      // index into RowN
         const float u_c = S.u[C].x[e], v_c = S.v[C].x[e];
-        const float F_c = S.F[C].x[e], k_c = S.kp[C].x[e], rho_c = S.rho[C].x[e], nu_c = S.nu[C][q];
+        const float F_c = S.F[C].x[e], k_c = S.kp[C].x[e], nu_c = S.nu[C][q];
         {   // ---- u*  (2dvof.py:208-220)
             const float u_m = S.u[M].x[e], u_p = S.u[P1].x[e], u_jm = S.u[C].x[e - 1], u_jp = S.u[C].x[e + 1];
             const float v_here = 0.25f * (((S.v[M].x[e] + S.v[M].x[e + 1]) + v_c) + S.v[C].x[e + 1]);
@@ -96,7 +99,9 @@ __device__ __forceinline__ void adv_row(const AdvState<INLINE_PROPS>& S, const M
                 const float kappa_ave = (k_c + S.kp[M].x[e]) / 2.0f;
                 const float t = (k.neg_sigma * dF) * kappa_ave;
                 const float fx_kappa = c.fast_div_ok ? div_by_const(t, c.d_dx) : t / k.dx;
-                acc = acc + (fx_kappa * 2.0f) / (rho_c + S.rho[M].x[e]);
+                const float rho_c = INLINE_PROPS ? rho_of(F_c, c.k) : rho[off + q];
+                const float rho_m = INLINE_PROPS ? rho_of(S.F[M].x[e], c.k) : rho[off + q - P];
+                acc = acc + (fx_kappa * 2.0f) / (rho_c + rho_m);
             }
             ou[q] = u_c + k.dt * acc;
         }
@@ -116,22 +121,27 @@ __device__ __forceinline__ void adv_row(const AdvState<INLINE_PROPS>& S, const M
                 const float kappa_ave = (k_c + S.kp[C].x[e - 1]) / 2.0f;
                 const float t = (k.neg_sigma * dF) * kappa_ave;
                 const float fy_kappa = c.fast_div_ok ? div_by_const(t, c.d_dy) : t / k.dy;
-                acc = acc + (fy_kappa * 2.0f) / (rho_c + S.rho[C].x[e - 1]);
+                const float rho_c = INLINE_PROPS ? rho_of(F_c, c.k) : rho[off + q];
+                const float rho_jm = INLINE_PROPS ? rho_of(S.F[C].x[e - 1], c.k) : rho[off + q - 1];
+                acc = acc + (fy_kappa * 2.0f) / (rho_c + rho_jm);
             }
             ov[q] = v_c + k.dt * acc;
         }
     }
     // u*: gi in [2, nx], j in [1, ny];  v*: gi in [1, nx], j in [2, ny].  Everything else is never written.
     const bool urow = gi >= 2 && gi <= nx, vrow = gi >= 1 && gi <= nx;
-    if (jl + 3 <= ny) {
-        if (urow) *reinterpret_cast<float4*>(us + off) = make_float4(ou[0], ou[1], ou[2], ou[3]);
+    if (jl + NC - 1 <= ny) {
+        if (urow) VecN<NC>::st(us + off, ou);
         if (vrow) {
-            if (jl >= 2) *reinterpret_cast<float4*>(vs + off) = make_float4(ov[0], ov[1], ov[2], ov[3]);
-            else { vs[off + 1] = ov[1]; vs[off + 2] = ov[2]; vs[off + 3] = ov[3]; }
+            if (jl >= 2) VecN<NC>::st(vs + off, ov);
+            else {
+#pragma unroll
+                for (int q = 1; q < NC; ++q) vs[off + q] = ov[q];
+            }
         }
     } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < NC; ++q) {
             const int j = jl + q;
             if (urow && j <= ny) us[off + q] = ou[q];
             if (vrow && j >= 2 && j <= ny) vs[off + q] = ov[q];
@@ -139,7 +149,7 @@ __device__ __forceinline__ void adv_row(const AdvState<INLINE_PROPS>& S, const M
     }
 }
 
-template <bool INLINE_PROPS>
+template <bool INLINE_PROPS, int NC>
 __global__ void __launch_bounds__(32 * kMomWarps)
 k_advect4(Grid g, MomC c, const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ F,
           const float* __restrict__ kappa, const float* __restrict__ rho, const float* __restrict__ nu,
@@ -150,24 +160,24 @@ k_advect4(Grid g, MomC c, const float* __restrict__ u, const float* __restrict__
     const int ia = r0 + chunk * rows_per_chunk;
     if (ia > r1) return;
     const int ib = min(r1, ia + rows_per_chunk - 1);
-    const int jl = 1 + 128 * strip + 4 * lane;
+    const int jl = 1 + 32 * NC * strip + NC * lane;
     const bool active = jl <= g.ny + 1;
     const int P = g.pitch;
     const size_t col = (size_t)jl;
-    AdvState<INLINE_PROPS> S;
+    AdvState<INLINE_PROPS, NC> S;
     // rows ia-1 and ia enter slots 1 and 2 (OLD and MID of phase 0)
-    adv_load<INLINE_PROPS, 1>(S, c, u, v, F, kappa, rho, nu, (size_t)(ia - 1) * P + col, lane, active);
-    adv_load<INLINE_PROPS, 2>(S, c, u, v, F, kappa, rho, nu, (size_t)ia * P + col, lane, active);
+    adv_load<INLINE_PROPS, NC, 1>(S, c, u, v, F, kappa, rho, nu, (size_t)(ia - 1) * P + col, lane, active);
+    adv_load<INLINE_PROPS, NC, 2>(S, c, u, v, F, kappa, rho, nu, (size_t)ia * P + col, lane, active);
     for (int i = ia; i <= ib; i += 3) {
         // every lane takes part in the shuffles of the loads; stores are guarded by `active` and the row range
-        adv_load<INLINE_PROPS, 0>(S, c, u, v, F, kappa, rho, nu, (size_t)min(i + 1, g.nrows - 1) * P + col, lane, active);
-        if (active) adv_row<INLINE_PROPS, 0>(S, c, us, vs, (size_t)i * P + col, g.gi0 + i, jl, g.nx, g.ny);
+        adv_load<INLINE_PROPS, NC, 0>(S, c, u, v, F, kappa, rho, nu, (size_t)min(i + 1, g.nrows - 1) * P + col, lane, active);
+        if (active) adv_row<INLINE_PROPS, NC, 0>(S, c, rho, P, us, vs, (size_t)i * P + col, g.gi0 + i, jl, g.nx, g.ny);
         if (i + 1 > ib) break;
-        adv_load<INLINE_PROPS, 1>(S, c, u, v, F, kappa, rho, nu, (size_t)min(i + 2, g.nrows - 1) * P + col, lane, active);
-        if (active) adv_row<INLINE_PROPS, 1>(S, c, us, vs, (size_t)(i + 1) * P + col, g.gi0 + i + 1, jl, g.nx, g.ny);
+        adv_load<INLINE_PROPS, NC, 1>(S, c, u, v, F, kappa, rho, nu, (size_t)min(i + 2, g.nrows - 1) * P + col, lane, active);
+        if (active) adv_row<INLINE_PROPS, NC, 1>(S, c, rho, P, us, vs, (size_t)(i + 1) * P + col, g.gi0 + i + 1, jl, g.nx, g.ny);
         if (i + 2 > ib) break;
-        adv_load<INLINE_PROPS, 2>(S, c, u, v, F, kappa, rho, nu, (size_t)min(i + 3, g.nrows - 1) * P + col, lane, active);
-        if (active) adv_row<INLINE_PROPS, 2>(S, c, us, vs, (size_t)(i + 2) * P + col, g.gi0 + i + 2, jl, g.nx, g.ny);
+        adv_load<INLINE_PROPS, NC, 2>(S, c, u, v, F, kappa, rho, nu, (size_t)min(i + 3, g.nrows - 1) * P + col, lane, active);
+        if (active) adv_row<INLINE_PROPS, NC, 2>(S, c, rho, P, us, vs, (size_t)(i + 2) * P + col, g.gi0 + i + 2, jl, g.nx, g.ny);
     }
 }
 
