@@ -144,7 +144,7 @@ int vof2d_profile_read(VofCtx* c, int kind, double* ms_total, int64_t* spans);  
 
 /* tuning knobs for A/B measurements (defaults = fast paths; results are identical either way) */
 enum {
-    VOF_OPT_JACOBI_TB = 0,    /* 1: <= 5 sweeps per HBM pass (default), 0: one launch per sweep */
+    VOF_OPT_JACOBI_TB = 0,    /* <= 5 sweeps per HBM pass: 0 never, 1 when p/rhs exceed L2 (default), 2 always */
     VOF_OPT_FCT_X_COLS = 1,   /* columns per lane of the x-sweep kernel: 2 (default) or 4 */
     VOF_OPT_ADVECT_COLS = 2   /* columns per lane of the momentum predictor: 2 (default) or 4 */
 };

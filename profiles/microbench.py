@@ -47,7 +47,7 @@ timeit("advect_upwind (2 cols/lane)", s.advect_upwind, 24)
 timeit("solve_p_jacobi(1)", lambda: s.solve_p_jacobi(1), 20)
 s.set_option(_lib.VOF_OPT_JACOBI_TB, 0)
 timeit("solve_p_jacobi(10) no TB (+rhs)", lambda: s.solve_p_jacobi(10), 12, 10)
-s.set_option(_lib.VOF_OPT_JACOBI_TB, 1)
+s.set_option(_lib.VOF_OPT_JACOBI_TB, 2)
 timeit("solve_p_jacobi(10) TB 5+5 (+rhs)", lambda: s.solve_p_jacobi(10), 12, 10)
 timeit("solve_p_jacobi(5) TB (+rhs)", lambda: s.solve_p_jacobi(5), 12, 5)
 timeit("update_uv", s.update_uv, 24)

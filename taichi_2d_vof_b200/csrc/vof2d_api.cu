@@ -325,8 +325,18 @@ struct Span {
     ~Span() { if (b) cudaEventRecord(b, c->stream); }
 };
 
-constexpr int kRowsPerBlock = 32;   // rows marched by one block of the streaming kernels
-constexpr int kFctRows = 96;        // x-sweep chunk (6 warm-up rows are re-read per chunk)
+// Rows marched by one warp / block of the streaming kernels.  Long chunks amortise the warm-up rows that a chunk
+// re-reads, but a grid needs ~16 resident warps per SM to hide latency: on big grids the cap `max_rows` applies,
+// on small ones the chunks shrink (down to `min_rows`) until there are enough of them.
+static int chunk_rows(const VofCtx* c, int rows, int columns_of_units, int min_rows, int max_rows, int units_per_warp = 1) {
+    const int target_warps = c->sm_count * 16;
+    const int warps_per_row_chunk = std::max(1, columns_of_units / units_per_warp);
+    const int nch = std::max(1, cdiv(target_warps, warps_per_row_chunk));
+    int r = cdiv(rows, nch);
+    r = std::max(r, min_rows);
+    r = std::min(r, max_rows);
+    return std::max(1, std::min(r, rows));
+}
 
 static unsigned bc_mask_all = 31u;
 
@@ -343,8 +353,9 @@ static int run_set_bc(VofCtx* c, unsigned mask) {
 static int run_cal_nu_rho(VofCtx* c) {
     Span span_(c, VOF_K_PROPS);
     const int rows = c->all_b - c->all_a + 1;
-    dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, kRowsPerBlock));
-    k_cal_nu_rho<<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_RHO], c->buf[BUF_NU], c->all_a, c->all_b, kRowsPerBlock);
+    const int rpb = chunk_rows(c, rows, cdiv(c->g.ny + 2, 32), 4, 32);
+    dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, rpb));
+    k_cal_nu_rho<<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_RHO], c->buf[BUF_NU], c->all_a, c->all_b, rpb);
     return launch_ok("k_cal_nu_rho");
 }
 
@@ -352,13 +363,12 @@ static int run_kappa(VofCtx* c) {
     Span span_(c, VOF_K_KAPPA);
     const int rows = c->in_b - c->in_a + 1;
     const int nstrips = cdiv(c->g.ny, kKapValid);
-    const int rpc = 64;
+    const int rpc = chunk_rows(c, rows, nstrips, 16, 64);
     dim3 grid(cdiv(nstrips * cdiv(rows, rpc), kKapWarps));
     k_kappa4<<<grid, 32 * kKapWarps, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_KAPPA], c->in_a, c->in_b, rpc, nstrips);
     return launch_ok("k_kappa4");
 }
 
-constexpr int kMomRows = 64;       // rows marched by one warp of the momentum kernels
 
 static int run_advect(VofCtx* c, bool inline_props) {
     Span span_(c, VOF_K_ADVECT);
@@ -366,8 +376,9 @@ static int run_advect(VofCtx* c, bool inline_props) {
     const int rows = b - a + 1;
     const int nc = c->opt_advect_cols;
     const int nstrips = cdiv(c->g.ny, 32 * nc);
-    dim3 grid(cdiv(nstrips * cdiv(rows, kMomRows), kMomWarps));
-#define ADA c->g, c->mom, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->buf[BUF_KAPPA], c->buf[BUF_RHO], c->buf[BUF_NU], c->buf[BUF_US], c->buf[BUF_VS], a, b, kMomRows, nstrips
+    const int rpc = chunk_rows(c, rows, nstrips, 8, 64);
+    dim3 grid(cdiv(nstrips * cdiv(rows, rpc), kMomWarps));
+#define ADA c->g, c->mom, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->buf[BUF_KAPPA], c->buf[BUF_RHO], c->buf[BUF_NU], c->buf[BUF_US], c->buf[BUF_VS], a, b, rpc, nstrips
     if (nc == 2) {
         if (inline_props) k_advect4<true, 2><<<grid, 32 * kMomWarps, 0, c->stream>>>(ADA);
         else k_advect4<false, 2><<<grid, 32 * kMomWarps, 0, c->stream>>>(ADA);
@@ -383,11 +394,12 @@ static int run_rhs(VofCtx* c, bool inline_props) {
     Span span_(c, VOF_K_RHS);
     const int a = c->in_a, b = std::min(c->in_b, c->g.nrows - 2);
     const int rows = b - a + 1;
-    dim3 grid(cdiv(c->g.ny, kBlockJ), cdiv(rows, kRowsPerBlock));
+    const int rpb = chunk_rows(c, rows, cdiv(c->g.ny, 32), 4, 32);
+    dim3 grid(cdiv(c->g.ny, kBlockJ), cdiv(rows, rpb));
     if (inline_props)
-        k_rhs<true><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_RHS], a, b, kRowsPerBlock);
+        k_rhs<true><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_RHS], a, b, rpb);
     else
-        k_rhs<false><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->buf[BUF_RHO], c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_RHS], a, b, kRowsPerBlock);
+        k_rhs<false><<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->buf[BUF_RHO], c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_RHS], a, b, rpb);
     c->rhs_valid = true;
     return launch_ok("k_rhs");
 }
@@ -396,9 +408,10 @@ static int run_rhs(VofCtx* c, bool inline_props) {
 static int run_jacobi_sweep(VofCtx* c, int rhs_mode) {
     Span span_(c, VOF_K_JACOBI);
     const int rows = c->all_b - c->all_a + 1;
-    dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, kRowsPerBlock));
+    const int rpb = chunk_rows(c, rows, cdiv(c->g.ny + 2, 32), 4, 32);
+    dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, rpb));
     const float* rhoF = rhs_mode == 2 ? c->F() : c->buf[BUF_RHO];
-#define JARGS c->g, c->k, c->p(), c->p_alt(), c->buf[BUF_RHS], rhoF, c->buf[BUF_US], c->buf[BUF_VS], c->all_a, c->all_b, kRowsPerBlock
+#define JARGS c->g, c->k, c->p(), c->p_alt(), c->buf[BUF_RHS], rhoF, c->buf[BUF_US], c->buf[BUF_VS], c->all_a, c->all_b, rpb
     if (rhs_mode == 0) k_jacobi<0><<<grid, kBlockJ, 0, c->stream>>>(JARGS);
     else if (rhs_mode == 1) k_jacobi<1><<<grid, kBlockJ, 0, c->stream>>>(JARGS);
     else k_jacobi<2><<<grid, kBlockJ, 0, c->stream>>>(JARGS);
@@ -429,6 +442,16 @@ static int launch_jacobi_tb(VofCtx* c, const float* pin, float* pout) {
     kern<<<cdiv(nwarps, kJacWarpsPerBlock), 32 * kJacWarpsPerBlock, 0, c->stream>>>(c->g, c->jac, sc, pin, pout, c->buf[BUF_RHS],
                                                                                   c->in_a, c->in_b);
     return launch_ok("k_jacobi_tb");
+}
+
+// Temporal blocking pays when p and rhs stream from HBM.  When they fit in the 126 MB L2 (<= ~2900^2 cells) the plain
+// one-sweep kernel runs from L2 and has far more parallelism than strips x chunks of a small grid.
+// opt_jacobi_tb: 0 = never, 1 = by grid size (default), 2 = always.
+static bool use_jacobi_tb(const VofCtx* c) {
+    if (c->opt_jacobi_tb == 0) return false;
+    if (c->opt_jacobi_tb == 2) return true;
+    const double mb = 3.0 * (double)c->g.nrows * c->g.pitch * sizeof(float) / 1e6;   // p, p', rhs
+    return mb > 100.0;
 }
 
 // nsweeps sweeps from the hoisted rhs, at most 5 per HBM pass; `frame`: keep ghost cells of p exact
@@ -464,16 +487,17 @@ static int run_project(VofCtx* c, bool inline_props) {
     const int a = std::max(c->in_a, 1), b = c->in_b;
     const int rows = b - a + 1;
     const int nstrips = cdiv(c->g.ny, 128);
-    dim3 grid(cdiv(nstrips * cdiv(rows, kMomRows), kMomWarps));
+    const int rpc = chunk_rows(c, rows, nstrips, 8, 64);
+    dim3 grid(cdiv(nstrips * cdiv(rows, rpc), kMomWarps));
     unsigned long long* cc = &c->diag->courant_count;
     CU(cudaMemsetAsync(cc, 0, sizeof(*cc), c->stream));
     const float* rhoF = inline_props ? c->F() : c->buf[BUF_RHO];
     if (inline_props)
         k_project4<true><<<grid, 32 * kMomWarps, 0, c->stream>>>(c->g, c->k, rhoF, c->p(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_U], c->buf[BUF_V],
-                                                               cc, a, b, kMomRows, nstrips, c->lo - c->g.gi0, c->hi - c->g.gi0);
+                                                               cc, a, b, rpc, nstrips, c->lo - c->g.gi0, c->hi - c->g.gi0);
     else
         k_project4<false><<<grid, 32 * kMomWarps, 0, c->stream>>>(c->g, c->k, rhoF, c->p(), c->buf[BUF_US], c->buf[BUF_VS], c->buf[BUF_U], c->buf[BUF_V],
-                                                                cc, a, b, kMomRows, nstrips, c->lo - c->g.gi0, c->hi - c->g.gi0);
+                                                                cc, a, b, rpc, nstrips, c->lo - c->g.gi0, c->hi - c->g.gi0);
     return launch_ok("k_project4");
 }
 
@@ -482,9 +506,10 @@ static int run_fct_x(VofCtx* c, bool post) {
     const int rows = c->in_b - c->in_a + 1;
     const int nc = c->opt_fct_x_cols;
     const int nstrips = cdiv(c->g.ny + 1, 32 * nc);
-    const int nwarps = nstrips * cdiv(rows, kFctRows);
+    const int rpc = chunk_rows(c, rows, nstrips, 24, 96);     // 6 warm-up rows are re-read per chunk
+    const int nwarps = nstrips * cdiv(rows, rpc);
     dim3 grid(cdiv(nwarps, kFctXWarps));
-#define FXA c->g, c->fctx, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, kFctRows, nstrips
+#define FXA c->g, c->fctx, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, rpc, nstrips
     if (nc == 2) {
         if (post) k_fct_x4<true, 2><<<grid, 32 * kFctXWarps, 0, c->stream>>>(FXA);
         else k_fct_x4<false, 2><<<grid, 32 * kFctXWarps, 0, c->stream>>>(FXA);
@@ -501,7 +526,7 @@ static int run_fct_y(VofCtx* c, bool post) {
     Span span_(c, VOF_K_FCT_Y);
     const int rows = c->all_b - c->all_a + 1;
     const int nstrips = cdiv(c->g.ny + 1, kFctYValid);
-    const int rpw = 16;
+    const int rpw = chunk_rows(c, rows, nstrips, 2, 16);
     const int nwarps = nstrips * cdiv(rows, rpw);
     dim3 grid(cdiv(nwarps, kFctYWarps));
     if (post) k_fct_y4<true><<<grid, 32 * kFctYWarps, 0, c->stream>>>(c->g, c->fcty, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b, rpw, nstrips);
@@ -513,8 +538,9 @@ static int run_fct_y(VofCtx* c, bool post) {
 static int run_post(VofCtx* c) {
     Span span_(c, VOF_K_POST);
     const int rows = c->all_b - c->all_a + 1;
-    dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, kRowsPerBlock));
-    k_post_process_f<<<grid, kBlockJ, 0, c->stream>>>(c->g, c->F(), c->all_a, c->all_b, kRowsPerBlock);
+    const int rpb = chunk_rows(c, rows, cdiv(c->g.ny + 2, 32), 4, 32);
+    dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, rpb));
+    k_post_process_f<<<grid, kBlockJ, 0, c->stream>>>(c->g, c->F(), c->all_a, c->all_b, rpb);
     return launch_ok("k_post_process_f");
 }
 
@@ -541,7 +567,7 @@ extern "C" int vof2d_solve_p_jacobi(VofCtx* c, int nsweeps) {
     if (nsweeps == 1) return run_jacobi_sweep(c, 1);   // the reference's structure: rhs recomputed inside the sweep
     if (nsweeps == 0) return VOF_OK;
     TRY(run_rhs(c, false));
-    if (c->opt_jacobi_tb) return run_jacobi_tb(c, nsweeps, true);
+    if (use_jacobi_tb(c)) return run_jacobi_tb(c, nsweeps, true);
     for (int s = 0; s < nsweeps; ++s) TRY(run_jacobi_sweep(c, 0));
     return VOF_OK;
 }
@@ -582,7 +608,7 @@ static int step_impl(VofCtx* c, int istep, unsigned flags) {
     TRY(run_advect(c, true));
     TRY(run_set_bc(c, mask));
     TRY(run_rhs(c, true));
-    if (c->opt_jacobi_tb && c->P.n_jacobi > 0) TRY(run_jacobi_tb(c, c->P.n_jacobi, false));
+    if (use_jacobi_tb(c) && c->P.n_jacobi > 0) TRY(run_jacobi_tb(c, c->P.n_jacobi, false));
     else for (int s = 0; s < c->P.n_jacobi; ++s) TRY(run_jacobi_sweep(c, 0));
     TRY(run_project(c, true));
     TRY(run_set_bc(c, mask));
@@ -818,7 +844,7 @@ extern "C" int vof2d_profile_read(VofCtx* c, int kind, double* ms_total, int64_t
 extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
     CHECK_CTX(c);
     switch (option) {
-        case VOF_OPT_JACOBI_TB: c->opt_jacobi_tb = value != 0; break;
+        case VOF_OPT_JACOBI_TB: if (value < 0 || value > 2) return fail(VOF_EINVAL, "jacobi_tb must be 0, 1 or 2"); c->opt_jacobi_tb = value; break;
         case VOF_OPT_ADVECT_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "advect columns per lane must be 2 or 4"); c->opt_advect_cols = value; break;
         case VOF_OPT_FCT_X_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "fct_x columns per lane must be 2 or 4"); c->opt_fct_x_cols = value; break;
         default: return fail(VOF_EINVAL, "unknown option %d", option);

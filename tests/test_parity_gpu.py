@@ -167,7 +167,9 @@ def test_jacobi_temporal_blocking_equals_single_sweeps(built_lib, nsweeps, shape
     o.p[...] = (rng.random(shp, dtype=np.float32) - 0.5) * 100.0
     o.p[5:9, 7:11] = 0.0
     o.p[20, 20] = 1e-36          # tiny numerators take the IEEE path of the reciprocal division
+    from taichi_2d_vof_b200 import _lib
     s = _solver(P)
+    s.set_option(_lib.VOF_OPT_JACOBI_TB, 2)      # force the blocked kernel (small grids default to single sweeps)
     for k in ("rho", "u_star", "v_star", "p"):
         getattr(s, k).from_numpy(getattr(o, k))
     for _ in range(nsweeps):
@@ -182,7 +184,7 @@ def test_jacobi_tb_on_off_identical(built_lib):
     from taichi_2d_vof_b200 import _lib
     P = Vof2DParams(nx=256, ny=384, Lx=0.128, Ly=0.192)
     outs = []
-    for tb in (1, 0):
+    for tb in (2, 0):
         s = _solver(P); s.set_option(_lib.VOF_OPT_JACOBI_TB, tb); s.set_init_F(3)
         for _ in range(6):
             s.step()
@@ -195,8 +197,12 @@ def test_jacobi_tb_on_off_identical(built_lib):
 def test_larger_grid_against_c_oracle(built_lib, ic):
     """1024 x 768 (many strips / chunks / tiles), 12 steps, fused path vs the C twin of the oracle."""
     P = Vof2DParams(nx=1024, ny=768, Lx=0.512, Ly=0.384)
+    from taichi_2d_vof_b200 import _lib
     o = Vof2DCOracle(P); o.set_init_F(ic); o.run(12)
-    s = _solver(P); s.set_init_F(ic); s.run(12)
+    s = _solver(P)
+    if ic == 3:
+        s.set_option(_lib.VOF_OPT_JACOBI_TB, 2)     # the temporally blocked path (default only beyond the L2 size)
+    s.set_init_F(ic); s.run(12)
     _compare(s, o, CORE, TOL_1STEP, tag="1024x768, 12 steps")
 
 
