@@ -31,6 +31,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_JACOBI = 10
+IC_NAMES = {1: "dam break", 2: "rising bubble", 3: "dropping liquid"}
 METRIC = "Jacobi Gcell-updates/s over whole timesteps (10 sweeps/step), 8192^2 cells per GPU"
 UNIT = "Gcell-updates/s"
 # algorithmic bytes per cell per launch (SURVEY.md 8d / DESIGN.md): fp32 arrays read + written once
@@ -167,15 +168,18 @@ def run_ours(args):
     n = args.n
     ny = n
     nx_global = n * world                      # weak scaling: 8192 rows per GPU
+    scaling = "weak"
+    if args.nx_global:                         # fixed global grid (BASELINE config 4: 32768^2 over 2/4/8 GPUs)
+        nx_global, ny, scaling = args.nx_global, (args.ny or args.nx_global), "strong"
     L_y, L_x = 0.1 * ny / 200.0, 0.1 * nx_global / 200.0
 
     def params_fn(slab, halo, device):
         from taichi_2d_vof_b200 import reference_params
         return reference_params(nx=nx_global, ny=ny, Lx=L_x, Ly=L_y, n_jacobi=N_JACOBI, slab=slab, halo=halo, device=device)
 
-    slab = SlabSolver2D(params_fn, nx_global, rank, world, dist=dist, n_jacobi=N_JACOBI, device=local)
+    slab = SlabSolver2D(params_fn, nx_global, rank, world, dist=dist, n_jacobi=N_JACOBI, device=local, transport=args.transport)
     s = slab.solver
-    slab.set_init_F(3)
+    slab.set_init_F(args.ic)
     stream = slab.stream
 
     def barrier():
@@ -304,11 +308,11 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "timesteps_per_s": args.steps / sec, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"dropping liquid (-ic 3), {n}^2 cells per GPU (global {nx_global} x {ny}), constant-dx scaling "
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{IC_NAMES[args.ic]} (-ic {args.ic}), {slab.hi - slab.lo + 1} x {ny} cells per GPU (global {nx_global} x {ny}), constant-dx scaling "
                                    f"L = 0.1*n/200, dt = 4e-6, {N_JACOBI} Jacobi sweeps/step, fused step (vof2d_step)",
                        "grid_per_gpu": [slab.hi - slab.lo + 1, ny], "global_grid": [nx_global, ny],
-                       "decomposition": "row slabs along i, deep halo %d rows, 1 exchange/step" % s.halo if world > 1 else "single GPU",
+                       "decomposition": ("row slabs along i, deep halo %d rows, 1 exchange/step, transport %s" % (s.halo, args.transport)) if world > 1 else "single GPU",
                        "l2": "inputs exceed L2 (10 live fp32 fields x %.0f MB >> 126 MB)" % (s.nrows * (ny + 2) * 4 / 1e6),
                        "rows_processed_per_launch": rows_local},
             "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
@@ -327,6 +331,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--n", type=int, default=8192, help="cells per side per GPU (default: the metric's 8192)")
+    ap.add_argument("--nx-global", type=int, default=0, help="fixed global rows (strong scaling) instead of --n rows per GPU")
+    ap.add_argument("--ny", type=int, default=0, help="columns with --nx-global (default: square)")
+    ap.add_argument("--ic", type=int, choices=[1, 2, 3], default=3)
+    ap.add_argument("--transport", choices=["p2p", "nccl"], default="p2p", help="halo exchange: NVLink peer stores + device flags, or NCCL send/recv")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -157,6 +157,16 @@ int vof2d_halo_ptr(VofCtx* c, int field, int side, int send, float** dev, int64_
 /* direct peer push: write my boundary rows into the neighbour's halo rows (peer-mapped memory) */
 int vof2d_halo_push(VofCtx* c, int field, int side, float* peer_halo_dst);
 
+/* NVLink peer-to-peer halo exchange (new): each rank maps its neighbours' arenas (CUDA IPC across processes, or a
+ * plain pointer inside one process) and vof2d_halo_exchange_p2p() stores its boundary rows of u, v, p, F straight
+ * into their halo rows with device-side flag hand-shakes -- stream-ordered, no NCCL, no host synchronisation.
+ * Every rank of the decomposition must call it once per step (before vof2d_step). */
+int vof2d_p2p_export(VofCtx* c, void* handle64, int64_t* nrows, int64_t* arena_bytes);   /* cudaIpcMemHandle_t */
+int vof2d_p2p_connect(VofCtx* c, int side, const void* handle64, void* same_process_arena, int64_t peer_nrows);
+int vof2d_p2p_arena(VofCtx* c, void** arena);
+int vof2d_halo_exchange_p2p(VofCtx* c);
+int vof2d_p2p_status(VofCtx* c, int* timed_out_epoch);   /* != 0: a wait gave up after 20 s (neighbour gone) */
+
 /* =====================================================================================
  * 3-D twin: the loop body of 3dvof.py:598-623.  Fields are the reference's (nx+2, ny+2, nz+2) fp32
  * arrays, index [i, j, k], k contiguous (3dvof.py:70-117); on the device element (i, j, k) is

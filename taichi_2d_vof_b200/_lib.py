@@ -98,6 +98,11 @@ SIGNATURES = {
     "vof2d_halo_rows": (C.c_int, [_ctx, _P(C.c_int), _P(C.c_int64)]),
     "vof2d_halo_ptr": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _P(C.c_void_p), _P(C.c_int64)]),
     "vof2d_halo_push": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p]),
+    "vof2d_p2p_export": (C.c_int, [_ctx, C.c_void_p, _P(C.c_int64), _P(C.c_int64)]),
+    "vof2d_p2p_connect": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]),
+    "vof2d_p2p_arena": (C.c_int, [_ctx, _P(C.c_void_p)]),
+    "vof2d_halo_exchange_p2p": (C.c_int, [_ctx]),
+    "vof2d_p2p_status": (C.c_int, [_ctx, _P(C.c_int)]),
     # ---- 3-D
     "vof3d_arena_bytes": (C.c_size_t, [_P(VofParams)]),
     "vof3d_create": (C.c_int, [_P(VofParams), _P(_ctx)]),

@@ -71,6 +71,10 @@ struct VofCtx {
     int opt_jacobi_tb;         // 1: temporal blocking (default), 0: one launch per sweep
     int opt_fct_x_cols;        // columns per lane of the x-sweep (2 or 4)
     int opt_advect_cols;       // columns per lane of the momentum predictor (2 or 4)
+    char* peer_arena[2];       // neighbour arenas mapped into this process (lower / upper), NVLink P2P
+    long long peer_nrows[2];
+    bool peer_ipc[2];
+    unsigned int p2p_epoch;
     int sm_count;
     // launch accounting + optional per-kernel-kind CUDA-event timing (vof2d_profile)
     long long launches;
@@ -273,6 +277,7 @@ extern "C" int vof2d_destroy(VofCtx* c) {
     for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 4; ++b)
             if (c->graph[a][b]) cudaGraphExecDestroy(c->graph[a][b]);
+    for (int sd = 0; sd < 2; ++sd) if (c->peer_arena[sd] && c->peer_ipc[sd]) cudaIpcCloseMemHandle(c->peer_arena[sd]);
     if (c->spans) { for (auto& sp : *c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); } delete c->spans; }
     if (c->ev_pool) { for (auto e : *c->ev_pool) cudaEventDestroy(e); delete c->ev_pool; }
     if (c->own_arena && c->arena) cudaFree(c->arena);
@@ -772,6 +777,49 @@ extern "C" int vof2d_diagnostics(VofCtx* c, double* mass, float* max_cfl, float*
 }
 
 // ------------------------------------------------------------------------------------
+// NVLink peer-to-peer halo exchange: kernels store straight into the neighbour's halo rows (peer-mapped
+// arena, CUDA IPC) and hand-shake through flags in the neighbour's memory -- no NCCL, no host synchronisation.
+// Per exchange (epoch e), all stream-ordered on the context's stream:
+//   signal done(e) to both neighbours ("my previous step no longer reads my halo rows")
+//   wait   done(e) from both neighbours, push my boundary rows of u, v, p, F into their halo rows,
+//   signal data(e), wait data(e) from both neighbours.
+// ------------------------------------------------------------------------------------
+struct P2PFlags { unsigned int done_from[2]; unsigned int data_from[2]; unsigned int timeout; unsigned int pad[3]; };
+
+__global__ void k_p2p_signal(unsigned int* lo_flag, unsigned int* hi_flag, unsigned int epoch) {
+    __threadfence_system();
+    if (lo_flag) *reinterpret_cast<volatile unsigned int*>(lo_flag) = epoch;
+    if (hi_flag) *reinterpret_cast<volatile unsigned int*>(hi_flag) = epoch;
+    __threadfence_system();
+}
+
+__global__ void k_p2p_wait(const unsigned int* a, const unsigned int* b, unsigned int epoch, unsigned int* timeout_flag) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int q = 0; q < 2; ++q) {
+        const volatile unsigned int* f = q == 0 ? a : b;
+        if (!f) continue;
+        while ((int)(*f - epoch) < 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > 20000000000ull) { *timeout_flag = epoch; return; }   // 20 s: a neighbour died; do not hang the GPU
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+
+// copy `count4` float4 per field from my send rows to the peer's halo rows; blockIdx.y = field * 2 + side
+struct P2PPush { const float4* src[8]; float4* dst[8]; };
+__global__ void __launch_bounds__(256)
+k_p2p_push(P2PPush a, long long count4) {
+    const float4* __restrict__ src = a.src[blockIdx.y];
+    float4* __restrict__ dst = a.dst[blockIdx.y];
+    if (!src || !dst) return;
+    for (long long k = blockIdx.x * 256ll + threadIdx.x; k < count4; k += (long long)gridDim.x * 256) dst[k] = src[k];
+}
+
+// ------------------------------------------------------------------------------------
 // slabs: halo rows are contiguous (rows * pitch floats, pad columns included)
 // ------------------------------------------------------------------------------------
 extern "C" int vof2d_halo_rows(const VofCtx* c, int* rows_per_side, int64_t* floats_per_field_side) {
@@ -852,5 +900,110 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
     for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 4; ++b)
             if (c->graph[a][b]) { cudaGraphExecDestroy(c->graph[a][b]); c->graph[a][b] = nullptr; }
+    return VOF_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// P2P halo exchange API
+// ------------------------------------------------------------------------------------
+static P2PFlags* flags_of(char* arena, size_t arena_bytes) { return (P2PFlags*)(arena + arena_bytes - 256 + 128); }
+
+extern "C" int vof2d_p2p_export(VofCtx* c, void* handle64, int64_t* nrows, int64_t* arena_bytes) {
+    CHECK_CTX(c);
+    if (!c->own_arena) return fail(VOF_ESTATE, "p2p export needs a library-owned (cudaMalloc) arena");
+    CU(cudaSetDevice(c->device));
+    if (handle64) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, c->arena));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(handle64, &h, 64);
+    }
+    if (nrows) *nrows = c->g.nrows;
+    if (arena_bytes) *arena_bytes = (int64_t)c->arena_bytes;
+    return VOF_OK;
+}
+
+static size_t arena_bytes_for_rows(const VofCtx* c, long long nrows) {
+    const size_t fb = field_stride_bytes((int)nrows, c->g.pitch);
+    const size_t xy = ((size_t)(c->P.nx + 3 + c->P.ny + 3) * sizeof(float) + 255) / 256 * 256;
+    return fb * BUF_COUNT + xy + 256;
+}
+
+extern "C" int vof2d_p2p_connect(VofCtx* c, int side, const void* handle64, void* same_process_arena, int64_t peer_nrows) {
+    CHECK_CTX(c);
+    if (side != 0 && side != 1) return fail(VOF_EINVAL, "side must be 0 or 1");
+    if ((side == 0 && c->has_lo) || (side == 1 && c->has_hi)) return fail(VOF_ESTATE, "side %d is a physical wall", side);
+    CU(cudaSetDevice(c->device));
+    if (same_process_arena) { c->peer_arena[side] = (char*)same_process_arena; c->peer_ipc[side] = false; }
+    else {
+        if (!handle64) return fail(VOF_EINVAL, "null IPC handle");
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle64, 64);
+        void* ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_arena[side] = (char*)ptr; c->peer_ipc[side] = true;
+    }
+    c->peer_nrows[side] = peer_nrows;
+    // CUDA loads kernels lazily and a first-use load may wait for the device to go idle: with a flag-waiting kernel
+    // already spinning that is a deadlock.  Load the hand-shake kernels now, while nothing waits.
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, k_p2p_signal));
+    CU(cudaFuncGetAttributes(&fa, k_p2p_wait));
+    CU(cudaFuncGetAttributes(&fa, k_p2p_push));
+    k_p2p_signal<<<1, 1, 0, c->stream>>>(nullptr, nullptr, 0u);
+    k_p2p_wait<<<1, 1, 0, c->stream>>>(nullptr, nullptr, 0u, &flags_of(c->arena, c->arena_bytes)->timeout);
+    P2PPush none; memset(&none, 0, sizeof(none));
+    k_p2p_push<<<dim3(1, 8), 256, 0, c->stream>>>(none, 0);
+    CU(cudaStreamSynchronize(c->stream));
+    return VOF_OK;
+}
+
+extern "C" int vof2d_p2p_arena(VofCtx* c, void** arena) { CHECK_CTX(c); if (arena) *arena = c->arena; return VOF_OK; }
+
+extern "C" int vof2d_halo_exchange_p2p(VofCtx* c) {
+    CHECK_CTX(c);
+    const bool nlo = !c->has_lo, nhi = !c->has_hi;
+    if (!nlo && !nhi) return VOF_OK;
+    if ((nlo && !c->peer_arena[0]) || (nhi && !c->peer_arena[1])) return fail(VOF_ESTATE, "vof2d_p2p_connect was not called for every neighbour");
+    CU(cudaSetDevice(c->device));
+    Span span_(c, VOF_K_HALO, 5);
+    const unsigned int e = ++c->p2p_epoch;
+    P2PFlags* mine = flags_of(c->arena, c->arena_bytes);
+    P2PFlags* plo = nlo ? flags_of(c->peer_arena[0], arena_bytes_for_rows(c, c->peer_nrows[0])) : nullptr;
+    P2PFlags* phi = nhi ? flags_of(c->peer_arena[1], arena_bytes_for_rows(c, c->peer_nrows[1])) : nullptr;
+    // I am the lower neighbour's upper side (index 1) and the upper neighbour's lower side (index 0)
+    k_p2p_signal<<<1, 1, 0, c->stream>>>(plo ? &plo->done_from[1] : nullptr, phi ? &phi->done_from[0] : nullptr, e);
+    k_p2p_wait<<<1, 1, 0, c->stream>>>(nlo ? &mine->done_from[0] : nullptr, nhi ? &mine->done_from[1] : nullptr, e, &mine->timeout);
+    P2PPush a;
+    memset(&a, 0, sizeof(a));
+    const int H = c->H, n = c->g.nrows, P = c->g.pitch;
+    const int fields[4] = {BUF_U, BUF_V, c->p_cur ? BUF_P1 : BUF_P0, c->F_cur ? BUF_F1 : BUF_F0};
+    for (int f = 0; f < 4; ++f) {
+        const size_t my_off = c->field_bytes * fields[f];
+        if (nlo) {   // my rows [H, 2H) -> lower neighbour's rows [n' - H, n')
+            const size_t pfb = field_stride_bytes((int)c->peer_nrows[0], P);
+            a.src[f * 2 + 0] = (const float4*)(c->arena + my_off + (size_t)H * P * sizeof(float));
+            a.dst[f * 2 + 0] = (float4*)(c->peer_arena[0] + pfb * fields[f] + (size_t)(c->peer_nrows[0] - H) * P * sizeof(float));
+        }
+        if (nhi) {   // my rows [n - 2H, n - H) -> upper neighbour's rows [0, H)
+            const size_t pfb = field_stride_bytes((int)c->peer_nrows[1], P);
+            a.src[f * 2 + 1] = (const float4*)(c->arena + my_off + (size_t)(n - 2 * H) * P * sizeof(float));
+            a.dst[f * 2 + 1] = (float4*)(c->peer_arena[1] + pfb * fields[f]);
+        }
+    }
+    const long long count4 = (long long)H * P / 4;     // pitch is a multiple of 32 floats
+    k_p2p_push<<<dim3(32, 8), 256, 0, c->stream>>>(a, count4);
+    k_p2p_signal<<<1, 1, 0, c->stream>>>(plo ? &plo->data_from[1] : nullptr, phi ? &phi->data_from[0] : nullptr, e);
+    k_p2p_wait<<<1, 1, 0, c->stream>>>(nlo ? &mine->data_from[0] : nullptr, nhi ? &mine->data_from[1] : nullptr, e, &mine->timeout);
+    return launch_ok("p2p halo exchange");
+}
+
+extern "C" int vof2d_p2p_status(VofCtx* c, int* timed_out_epoch) {
+    CHECK_CTX(c);
+    CU(cudaSetDevice(c->device));
+    unsigned int t = 0;
+    CU(cudaMemcpyAsync(&t, &flags_of(c->arena, c->arena_bytes)->timeout, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (timed_out_epoch) *timed_out_epoch = (int)t;
     return VOF_OK;
 }

@@ -68,7 +68,7 @@ class SlabSolver2D:
     """One rank's slab of a global (nx, ny) domain.  ``step()`` = halo exchange + the fused step."""
 
     def __init__(self, global_params_fn, nx: int, rank: int, nranks: int, dist=None, halo: int | None = None,
-                 n_jacobi: int = 10, device: int = -1):
+                 n_jacobi: int = 10, device: int = -1, transport: str = "p2p"):
         import torch
         from .solver2d import VofSolver2D
         self.rank, self.nranks, self.dist = rank, nranks, dist
@@ -83,6 +83,18 @@ class SlabSolver2D:
         self.solver = VofSolver2D(params, stream=self.stream)
         self.halo = self.solver.halo
         self._views = None
+        self.transport = transport if nranks > 1 else "none"
+        if self.transport == "p2p":
+            # map the neighbours' arenas (CUDA IPC): halo rows are then stored straight over NVLink by
+            # vof2d_halo_exchange_p2p, hand-shaking through device-side flags -- no NCCL call per step
+            mine = self.solver.p2p_export()
+            allh = [None] * nranks
+            dist.all_gather_object(allh, mine)
+            if rank > 0:
+                self.solver.p2p_connect(0, handle=allh[rank - 1][0], peer_nrows=allh[rank - 1][1])
+            if rank < nranks - 1:
+                self.solver.p2p_connect(1, handle=allh[rank + 1][0], peer_nrows=allh[rank + 1][1])
+            dist.barrier()
 
     def _halo_views(self):
         """torch views of the 4 x 4 halo blocks (whole pitched rows, contiguous)."""
@@ -105,6 +117,9 @@ class SlabSolver2D:
 
     def exchange_halos(self):
         if self.nranks == 1:
+            return
+        if self.transport == "p2p":
+            self.solver.halo_exchange_p2p()
             return
         import torch
         v = self._halo_views()   # re-queried every step: F and p ping-pong between two buffers
@@ -131,7 +146,7 @@ class LocalSlabGroup:
     the single-GPU parity test of the decomposition; the multi-process runner is SlabSolver2D."""
 
     def __init__(self, params_fn, nx: int, nslabs: int, halo: int | None = None, n_jacobi: int = 10, devices=None,
-                 solver_cls=None, halo_fields=HALO_FIELDS):
+                 solver_cls=None, halo_fields=HALO_FIELDS, p2p=False):
         if solver_cls is None:
             from .solver2d import VofSolver2D as solver_cls
         self.parts = partition(nx, nslabs)
@@ -141,9 +156,20 @@ class LocalSlabGroup:
                                              device=devices[r])) for r in range(nslabs)]
         self.nslabs = nslabs
         self.halo_fields = halo_fields
+        self.p2p = p2p and nslabs > 1
+        if self.p2p:
+            for r in range(nslabs):
+                if r > 0:
+                    self.solvers[r].p2p_connect(0, arena_ptr=self.solvers[r - 1].p2p_arena(), peer_nrows=self.solvers[r - 1].nrows)
+                if r < nslabs - 1:
+                    self.solvers[r].p2p_connect(1, arena_ptr=self.solvers[r + 1].p2p_arena(), peer_nrows=self.solvers[r + 1].nrows)
 
     def exchange_halos(self):
         S = self.solvers
+        if self.p2p:                   # device-side hand-shake: no host synchronisation at all
+            for s in S:
+                s.halo_exchange_p2p()
+            return
         for s in S:
             s.synchronize()            # the producers of the rows about to be copied
         for r in range(self.nslabs - 1):

@@ -263,5 +263,29 @@ class VofSolver2D:
         check(self._L.vof2d_halo_ptr(self._h, _lib.FIELD_IDS[name], side, 1 if send else 0, C.byref(dev), C.byref(n)))
         return dev.value, n.value
 
+    def p2p_export(self):
+        """(64-byte CUDA IPC handle of this context's arena, local rows)."""
+        buf = (C.c_ubyte * 64)()
+        n, nb = C.c_int64(), C.c_int64()
+        check(self._L.vof2d_p2p_export(self._h, buf, C.byref(n), C.byref(nb)))
+        return bytes(buf), n.value
+
+    def p2p_arena(self):
+        a = C.c_void_p()
+        check(self._L.vof2d_p2p_arena(self._h, C.byref(a)))
+        return a.value
+
+    def p2p_connect(self, side, handle=None, arena_ptr=None, peer_nrows=0):
+        hb = (C.c_ubyte * 64).from_buffer_copy(handle) if handle is not None else None
+        check(self._L.vof2d_p2p_connect(self._h, side, hb, C.c_void_p(arena_ptr) if arena_ptr else None, int(peer_nrows)))
+
+    def halo_exchange_p2p(self):
+        check(self._L.vof2d_halo_exchange_p2p(self._h))
+
+    def p2p_status(self):
+        t = C.c_int()
+        check(self._L.vof2d_p2p_status(self._h, C.byref(t)))
+        return t.value
+
     def halo_push(self, name, side, peer_dst):
         check(self._L.vof2d_halo_push(self._h, _lib.FIELD_IDS[name], side, C.c_void_p(peer_dst)))

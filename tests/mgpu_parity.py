@@ -25,7 +25,8 @@ def params_fn(slab, halo, device):
     return reference_params(nx=nx, ny=ny, Lx=0.1 * nx / 200, Ly=0.1 * ny / 200, slab=slab, halo=halo, device=device)
 
 
-s = SlabSolver2D(params_fn, nx, rank, world, dist=dist, device=local)
+transport = os.environ.get("VOF_TRANSPORT", "p2p")
+s = SlabSolver2D(params_fn, nx, rank, world, dist=dist, device=local, transport=transport)
 s.set_init_F(ic)
 for _ in range(steps):
     s.step()
@@ -54,7 +55,7 @@ dist.all_reduce(m)
 if rank == 0:
     print("global volume", float(m), "single-GPU", full.mass())
     ok = ok and abs(float(m) - full.mass()) <= 1e-9 * full.mass()
-    print("MGPU PARITY", "OK" if ok else "FAILED", f"({world} ranks, {nx}x{ny}, {steps} steps)")
+    print("MGPU PARITY", "OK" if ok else "FAILED", f"({world} ranks, {nx}x{ny}, {steps} steps, transport {transport})")
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

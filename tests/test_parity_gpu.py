@@ -207,6 +207,27 @@ def test_larger_grid_against_c_oracle(built_lib, ic):
 
 
 @pytest.mark.parametrize("nslabs", [2, 3])
+def test_row_slabs_p2p_flags_equal_full_domain(built_lib, nslabs):
+    """The NVLink-P2P exchange path (kernel stores into the neighbour's arena + device-side flag hand-shake, no host
+    synchronisation) on one device: slabs of unequal height, 30 steps, identical to the single-domain run."""
+    from taichi_2d_vof_b200 import VofSolver2D, reference_params
+    from taichi_2d_vof_b200.slab import LocalSlabGroup
+    nx, ny = 200, 64
+
+    def params_fn(slab, halo, device):
+        return reference_params(nx=nx, ny=ny, Lx=0.1 * nx / 200, Ly=0.1 * ny / 200, slab=slab, halo=halo, device=device)
+
+    full = VofSolver2D(params_fn(None, 0, 0)); full.set_init_F(3)
+    grp = LocalSlabGroup(params_fn, nx, nslabs, p2p=True); grp.set_init_F(3)
+    for step in range(30):
+        full.step(); grp.step()
+    for s in grp.solvers:
+        assert s.p2p_status() == 0
+    for k in ("F", "u", "v", "p"):
+        assert np.array_equal(grp.gather(k), getattr(full, k).to_numpy()), k
+
+
+@pytest.mark.parametrize("nslabs", [2, 3])
 @pytest.mark.parametrize("ic", [1, 3])
 def test_row_slabs_equal_full_domain(built_lib, nslabs, ic):
     """Row-slab decomposition with deep halos (one exchange per step) must reproduce the single-domain
