@@ -122,7 +122,7 @@ static __device__ __noinline__ float4 jac_general_row(float4 up, float4 md, floa
 
 // one row step: input row R (stage-0 values `pin`, and rhs of row R-1 in `rin`) enters the pipeline,
 // sweep s produces row R - s, the last sweep's row R - T is stored.
-template <int T, int PH, bool EDGE, bool FAST_DIV>
+template <int T, int PH, bool EDGE, bool FAST_DIV, bool WALLROWS>
 __device__ __forceinline__ void jac_step(JacPipe<T>& S, const JacEdge& E, const float4 pin, const float4 rin, const int R,
                                          const Grid& g, const JacTB& jc, const int jl, float* __restrict__ pout,
                                          const int ra, const int rb, const bool store_lane) {
@@ -145,7 +145,9 @@ __device__ __forceinline__ void jac_step(JacPipe<T>& S, const JacEdge& E, const 
         const float left = __shfl_up_sync(0xffffffffu, md[3], 1);     // p[i, j-1] of column 0
         const float right = __shfl_down_sync(0xffffffffu, md[0], 1);  // p[i, j+1] of column 3
         float out[4];
-        if (gi >= 2 && gi <= g.nx - 1) {     // ae = aw = cx (warp-uniform test)
+        // items whose rows stay away from the i-walls (WALLROWS = false: almost all of them) carry no fallback code at
+        // all, which keeps the hot loop body small enough for the instruction cache
+        if (!WALLROWS || (gi >= 2 && gi <= g.nx - 1)) {     // ae = aw = cx (warp-uniform test)
             float t[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -202,7 +204,7 @@ struct JacSched {          // work item -> (strip, chunk); warps pull items from
     unsigned int* counter; // zeroed by the host before the launch
 };
 
-template <int T, bool EDGE, bool FAST_DIV>
+template <int T, bool EDGE, bool FAST_DIV, bool WALLROWS>
 __device__ __forceinline__ void jac_run(const Grid& g, const JacTB& jc, const float* __restrict__ p, float* __restrict__ pout,
                                         const float* __restrict__ rhs, const int ra, const int rb, const int jstrip,
                                         const int lane) {
@@ -240,9 +242,9 @@ __device__ __forceinline__ void jac_run(const Grid& g, const JacTB& jc, const fl
     for (; R <= rb + T; R += 3) {
         const float4 pb0 = ldp(R + 3), pb1 = ldp(R + 4), pb2 = ldp(R + 5);
         const float4 qb0 = ldr(R + 2), qb1 = ldr(R + 3), qb2 = ldr(R + 4);
-        jac_step<T, 0, EDGE, FAST_DIV>(S, E, pa0, qa0, R, g, jc, jl, pout, ra, rb, store_lane);
-        jac_step<T, 1, EDGE, FAST_DIV>(S, E, pa1, qa1, R + 1, g, jc, jl, pout, ra, rb, store_lane);
-        jac_step<T, 2, EDGE, FAST_DIV>(S, E, pa2, qa2, R + 2, g, jc, jl, pout, ra, rb, store_lane);
+        jac_step<T, 0, EDGE, FAST_DIV, WALLROWS>(S, E, pa0, qa0, R, g, jc, jl, pout, ra, rb, store_lane);
+        jac_step<T, 1, EDGE, FAST_DIV, WALLROWS>(S, E, pa1, qa1, R + 1, g, jc, jl, pout, ra, rb, store_lane);
+        jac_step<T, 2, EDGE, FAST_DIV, WALLROWS>(S, E, pa2, qa2, R + 2, g, jc, jl, pout, ra, rb, store_lane);
         pa0 = pb0; pa1 = pb1; pa2 = pb2; qa0 = qb0; qa1 = qb1; qa2 = qb2;
     }
 }
@@ -266,8 +268,15 @@ k_jacobi_tb(Grid g, JacTB jc, JacSched sc, const float* __restrict__ p, float* _
         const int rb = min(r1, ra + sc.rpc - 1);
         const int jstrip = 1 - kJacStripMargin + strip * kJacStripValid;   // == 1 (mod 4): float4-aligned
         const bool strip_interior = jstrip >= 2 && jstrip + kJacStripCols - 1 <= g.ny - 1;
-        if (strip_interior) jac_run<T, false, FAST_DIV>(g, jc, p, pout, rhs, ra, rb, jstrip, lane);
-        else jac_run<T, true, FAST_DIV>(g, jc, p, pout, rhs, ra, rb, jstrip, lane);
+        // every row the pipeline touches (ra - T .. rb + T, minus the sweeps' skew) strictly inside the i-walls?
+        const bool wallrows = g.gi0 + ra - T - T < 2 || g.gi0 + rb + T > g.nx - 1;
+        if (strip_interior) {
+            if (wallrows) jac_run<T, false, FAST_DIV, true>(g, jc, p, pout, rhs, ra, rb, jstrip, lane);
+            else jac_run<T, false, FAST_DIV, false>(g, jc, p, pout, rhs, ra, rb, jstrip, lane);
+        } else {
+            if (wallrows) jac_run<T, true, FAST_DIV, true>(g, jc, p, pout, rhs, ra, rb, jstrip, lane);
+            else jac_run<T, true, FAST_DIV, false>(g, jc, p, pout, rhs, ra, rb, jstrip, lane);
+        }
     }
 }
 
