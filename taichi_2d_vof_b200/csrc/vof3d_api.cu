@@ -15,6 +15,7 @@ struct Vof3Ctx {
     Grid3 g;
     Consts3 k;
     Fct3C fct[3];
+    Jac3C jac;
     int device;
     cudaStream_t stream;
     bool own_stream;
@@ -116,6 +117,9 @@ extern "C" int vof3d_create(const VofParams* in, Vof3Ctx** out) {
                 volatile float s = ae + aw; s = s + an; s = s + as; s = s + ab; s = s + af;
                 k.ap[iw][jw][kw] = -1.0f * s;
             }
+    c->jac.cx = k.dxi2; c->jac.cy = k.dyi2; c->jac.cz = k.dzi2;
+    c->jac.dv = vofhost::make_const_div(k.ap[0][0][0]);
+    c->jac.fast_div_ok = 0;
     for (int ax = 0; ax < 3; ++ax) {
         Fct3C& f = c->fct[ax];
         f.dt = k.dt; f.dx = k.dx; f.dy = k.dy; f.dz = k.dz; f.vol = k.vol;
@@ -146,6 +150,15 @@ extern "C" int vof3d_create(const VofParams* in, Vof3Ctx** out) {
     CU(cudaMemcpy(c->zs, z.data(), z.size() * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
+    {   // prove the reciprocal division by the interior diagonal exact (every fp32 numerator against __fdiv_rn)
+        unsigned long long* bad = &c->diag->courant_count;
+        k_check_div_by_const<<<prop.multiProcessorCount * 8, 256, 0, c->stream>>>(c->jac.dv, bad);
+        unsigned long long h = 1;
+        CU(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
+        c->jac.fast_div_ok = (h == 0);
+    }
     *out = c;
     return VOF_OK;
 }
@@ -223,8 +236,10 @@ static int run3_jacobi(Vof3Ctx* c, int mode) {
     const int planes = c->all_b - c->all_a + 1;
     dim3 grid = grid_jk(c, c->g.nz + 2, c->g.ny + 2, planes, kRows3);
 #define J3 c->g, c->k, c->p(), c->p_alt(), c->buf[B3_RHS], c->buf[B3_RHO], c->buf[B3_US], c->buf[B3_VS], c->buf[B3_WS], c->all_a, c->all_b, kRows3
-    if (mode == 0) k3_jacobi<0><<<grid, kB3, 0, c->stream>>>(J3);
-    else k3_jacobi<1><<<grid, kB3, 0, c->stream>>>(J3);
+    if (mode == 0) {
+        dim3 g4(cdiv(c->g.nz + 1, 128), cdiv(c->g.ny + 2, 4), cdiv(planes, kRows3));
+        k3_jacobi4<<<g4, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, kRows3);
+    } else k3_jacobi<1><<<grid, kB3, 0, c->stream>>>(J3);
 #undef J3
     c->p_cur ^= 1;
     return launch_ok("k3_jacobi");

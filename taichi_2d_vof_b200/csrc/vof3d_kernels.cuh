@@ -209,6 +209,81 @@ k3_jacobi(Grid3 g, Consts3 c, const float* __restrict__ p, float* __restrict__ p
     }
 }
 
+// One sweep, 4 consecutive k per lane (LDG.128 / STG.128), hoisted rhs.  Cells away from every wall use literal
+// coefficients and the exact reciprocal division (ConstDiv, verified at context creation); the rest (wall
+// rows / columns, ghosts) take the selected-coefficient IEEE path.  Same arithmetic, same order.
+struct Jac3C { float cx, cy, cz; ConstDiv dv; int fast_div_ok; };
+
+__global__ void __launch_bounds__(128)
+k3_jacobi4(Grid3 g, Consts3 c, Jac3C jc, const float* __restrict__ p, float* __restrict__ pn, const float* __restrict__ rhs,
+           int r0, int r1, int rows_per_block) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 5);
+    const int kl = 1 + (blockIdx.x * 32 + lane) * 4;                      // == 1 (mod 4): 16-byte aligned
+    if (j > g.ny + 1) return;
+    const bool active = kl <= g.nz + 1;
+    const int ia = r0 + blockIdx.z * rows_per_block, ib = min(r1, ia + rows_per_block - 1);
+    if (ia > ib) return;
+    const size_t si = (size_t)g.pj, sj = (size_t)g.pk;
+    size_t o = (size_t)ia * si + (size_t)j * sj + kl;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto ld = [&](const float* b, size_t q) { return active ? *reinterpret_cast<const float4*>(b + q) : z4; };
+    const bool jin = j >= 1 && j <= g.ny;
+    const bool lane_interior = j >= 2 && j <= g.ny - 1 && kl >= 2 && kl + 3 <= g.nz - 1;   // no j- or k-wall coefficient is zero
+    float4 p_m = ia > 0 ? ld(p, o - si) : z4, p_c = ld(p, o);
+    for (int i = ia; i <= ib; ++i, o += si) {
+        const int gi = g.gi0 + i;
+        const float4 p_p = (i + 1 < g.nrows) ? ld(p, o + si) : z4;
+        // k-neighbours of the 4 cells: own values, the two outer ones from the adjacent lanes (or memory at the strip edge)
+        float left = __shfl_up_sync(0xffffffffu, p_c.w, 1), right = __shfl_down_sync(0xffffffffu, p_c.x, 1);
+        if (active) {
+            if (lane == 0) left = p[o - 1];
+            if (lane == 31 && kl + 4 <= g.nz + 1) right = p[o + 4];
+        }
+        float4 out = p_c;
+        if (active && jin && gi >= 1 && gi <= g.nx) {
+            const float4 pjp = ld(p, o + sj), pjm = ld(p, o - sj), b4 = ld(rhs, o);
+            const float pc[4] = {p_c.x, p_c.y, p_c.z, p_c.w}, pp[4] = {p_p.x, p_p.y, p_p.z, p_p.w}, pm[4] = {p_m.x, p_m.y, p_m.z, p_m.w};
+            const float jp[4] = {pjp.x, pjp.y, pjp.z, pjp.w}, jm[4] = {pjm.x, pjm.y, pjm.z, pjm.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            float r[4];
+            if (lane_interior && gi >= 2 && gi <= g.nx - 1) {
+                float t[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float kp = q < 3 ? pc[q + 1] : right, km = q > 0 ? pc[q - 1] : left;
+                    t[q] = bb[q] - jc.cx * pp[q];
+                    t[q] = t[q] - jc.cx * pm[q];
+                    t[q] = t[q] - jc.cy * jp[q];
+                    t[q] = t[q] - jc.cy * jm[q];
+                    t[q] = t[q] - jc.cz * kp;
+                    t[q] = t[q] - jc.cz * km;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) r[q] = jc.fast_div_ok ? div_by_const(t[q], jc.dv) : t[q] / jc.dv.b;
+            } else {
+                const float ae = (gi != g.nx) ? c.dxi2 : 0.0f, aw = (gi != 1) ? c.dxi2 : 0.0f;
+                const float an = (j != g.ny) ? c.dyi2 : 0.0f, as = (j != 1) ? c.dyi2 : 0.0f;
+                const int iw = (gi == 1 || gi == g.nx) ? 1 : 0, jw = (j == 1 || j == g.ny) ? 1 : 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k = kl + q;
+                    const float kp = q < 3 ? pc[q + 1] : right, km = q > 0 ? pc[q - 1] : left;
+                    const float af = (k != g.nz) ? c.dzi2 : 0.0f, ab = (k != 1) ? c.dzi2 : 0.0f;
+                    const float ap = c.ap[iw][jw][(k == 1 || k == g.nz) ? 1 : 0];
+                    float t = bb[q] - ae * pp[q];
+                    t = t - aw * pm[q]; t = t - an * jp[q]; t = t - as * jm[q];
+                    t = t - af * kp; t = t - ab * km;
+                    r[q] = (k >= 1 && k <= g.nz) ? t / ap : pc[q];        // ghost / pad columns pass through
+                }
+            }
+            out = make_float4(r[0], r[1], r[2], r[3]);
+        }
+        if (active) *reinterpret_cast<float4*>(pn + o) = out;
+        if (kl == 1 && active) pn[o - 1] = p[o - 1];                      // ghost column k = 0 passes through
+        p_m = p_c; p_c = p_p;
+    }
+}
+
 // ---- update_uv (3dvof.py:286-302) -----------------------------------------------------------------------------------
 template <bool INLINE_PROPS>
 __global__ void __launch_bounds__(kB3)
