@@ -68,9 +68,11 @@ class SlabSolver2D:
     """One rank's slab of a global (nx, ny) domain.  ``step()`` = halo exchange + the fused step."""
 
     def __init__(self, global_params_fn, nx: int, rank: int, nranks: int, dist=None, halo: int | None = None,
-                 n_jacobi: int = 10, device: int = -1, transport: str = "p2p"):
+                 n_jacobi: int = 10, device: int = -1, transport: str = "p2p", solver_cls=None, halo_fields=HALO_FIELDS):
         import torch
-        from .solver2d import VofSolver2D
+        if solver_cls is None:
+            from .solver2d import VofSolver2D as solver_cls
+        self.halo_fields = halo_fields
         self.rank, self.nranks, self.dist = rank, nranks, dist
         self.parts = partition(nx, nranks)
         self.lo, self.hi = self.parts[rank]
@@ -80,10 +82,12 @@ class SlabSolver2D:
         else:
             params = global_params_fn(slab=(self.lo, self.hi), halo=H, device=device)
         self.stream = torch.cuda.Stream(device=device if device >= 0 else None)
-        self.solver = VofSolver2D(params, stream=self.stream)
+        self.solver = solver_cls(params, stream=self.stream)
         self.halo = self.solver.halo
         self._views = None
         self.transport = transport if nranks > 1 else "none"
+        if self.transport == "p2p" and not hasattr(self.solver, "p2p_export"):
+            self.transport = "nccl"     # the 3-D context has no peer-store exchange yet
         if self.transport == "p2p":
             # map the neighbours' arenas (CUDA IPC): halo rows are then stored straight over NVLink by
             # vof2d_halo_exchange_p2p, hand-shaking through device-side flags -- no NCCL call per step
@@ -105,13 +109,13 @@ class SlabSolver2D:
             for send in (1, 0):
                 lst = []
                 if has_nbr:
-                    for name in HALO_FIELDS:
+                    for name in self.halo_fields:
                         addr, n = s.halo_ptr(name, side, send)
 
                         class _Blob:
                             __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (addr, False),
                                                         "version": 3, "strides": None}
-                        lst.append(torch.as_tensor(_Blob(), device=f"cuda:{s.device}"))
+                        lst.append(torch.as_tensor(_Blob(), device=f"cuda:{torch.cuda.current_device()}"))
                 views[(side, send)] = lst
         return views
 
@@ -136,7 +140,7 @@ class SlabSolver2D:
     def owned(self, name):
         """This rank's owned interior rows of a field, as numpy (rows lo..hi, all columns)."""
         a = getattr(self.solver, name).to_numpy()
-        H = self.solver.halo
+        H = self.solver.halo if self.nranks > 1 else 1
         return a[H:a.shape[0] - H]
 
 
