@@ -120,6 +120,21 @@ int vof2d_step_host(VofCtx* c, int istep, unsigned flags,
                     const float* u_in, const float* v_in, const float* p_in, const float* F_in,
                     float* u_out, float* v_out, float* p_out, float* F_out);
 
+/* ---- streamed host-buffer step (new): the state stays in HOST memory; the domain is cut into `n_slabs`
+ * row slabs (deep halo, as for multi-GPU) and upload of slab s+1, the step of slab s and download of slab
+ * s-1 overlap on three streams.  Same result as vof2d_step_host, bit for bit.  `p` are full-domain params.
+ * The arrays are dense (nx+2)*(ny+2) floats; *_out may alias *_in (in-place).  Pinned host memory is
+ * needed for the overlap (pageable memory works, serialised by the driver).  Synchronous.
+ * Replaces the to_numpy()/from_numpy() round trip a host-resident caller of the reference pays
+ * (2dvof.py:535, 565) around 2dvof.py:513-528. */
+typedef struct VofStreamer VofStreamer;
+int vof2d_streamer_create(const VofParams* p, int n_slabs, VofStreamer** out);
+int vof2d_streamer_destroy(VofStreamer* st);
+int vof2d_streamer_info(const VofStreamer* st, int* n_slabs, int* halo, size_t* device_bytes);
+int vof2d_streamer_step_host(VofStreamer* st, int istep, unsigned flags,
+                             const float* u_in, const float* v_in, const float* p_in, const float* F_in,
+                             float* u_out, float* v_out, float* p_out, float* F_out);
+
 /* ---- field access (replaces: field.to_numpy()/from_numpy(), 2dvof.py:535, 565) ---- */
 int vof2d_field_ptr(VofCtx* c, int field, float** dev, int64_t* pitch_elems, int64_t* rows);
 int vof2d_field_get(VofCtx* c, int field, float* host_dst);        /* logical rows of this ctx */

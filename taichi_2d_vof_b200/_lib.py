@@ -86,6 +86,10 @@ SIGNATURES = {
     "vof2d_step": (C.c_int, [_ctx, C.c_int, C.c_uint]),
     "vof2d_run": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_uint]),
     "vof2d_step_host": (C.c_int, [_ctx, C.c_int, C.c_uint] + [C.c_void_p] * 8),
+    "vof2d_streamer_create": (C.c_int, [_P(VofParams), C.c_int, _P(C.c_void_p)]),
+    "vof2d_streamer_destroy": (C.c_int, [C.c_void_p]),
+    "vof2d_streamer_info": (C.c_int, [C.c_void_p, _P(C.c_int), _P(C.c_int), _P(C.c_size_t)]),
+    "vof2d_streamer_step_host": (C.c_int, [C.c_void_p, C.c_int, C.c_uint] + [C.c_void_p] * 8),
     "vof2d_field_ptr": (C.c_int, [_ctx, C.c_int, _P(C.c_void_p), _P(C.c_int64), _P(C.c_int64)]),
     "vof2d_field_get": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
     "vof2d_field_set": (C.c_int, [_ctx, C.c_int, C.c_void_p]),

@@ -1007,3 +1007,123 @@ extern "C" int vof2d_p2p_status(VofCtx* c, int* timed_out_epoch) {
     if (timed_out_epoch) *timed_out_epoch = (int)t;
     return VOF_OK;
 }
+
+// ------------------------------------------------------------------------------------
+// Streamed host-buffer step: the state lives in HOST memory (as it does for a caller of the reference who
+// round-trips through to_numpy()/from_numpy(), 2dvof.py:535/565); the domain is cut into row slabs with the
+// same deep halo the multi-GPU decomposition uses, and slab s+1 is uploaded while slab s is computed and
+// slab s-1 is downloaded -- three streams, PCIe used in both directions at once.  Each slab's step is the
+// ordinary slab step (bit-identical to the full-domain step, see tests), fed its halo rows from the host
+// state instead of from a neighbour.
+// ------------------------------------------------------------------------------------
+struct VofStreamer {
+    int device = 0, nx = 0, ny = 0, H = 0;
+    std::vector<VofCtx*> slab;
+    cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_run;
+};
+
+extern "C" int vof2d_streamer_destroy(VofStreamer* st) {
+    if (!st) return VOF_OK;
+    cudaSetDevice(st->device);
+    if (st->s_in) cudaStreamSynchronize(st->s_in);
+    if (st->s_out) cudaStreamSynchronize(st->s_out);
+    for (VofCtx* c : st->slab) vof2d_destroy(c);       // synchronises s_run; a caller-provided stream is left alone
+    for (auto e : st->ev_in) cudaEventDestroy(e);
+    for (auto e : st->ev_run) cudaEventDestroy(e);
+    if (st->s_in) cudaStreamDestroy(st->s_in);
+    if (st->s_run) cudaStreamDestroy(st->s_run);
+    if (st->s_out) cudaStreamDestroy(st->s_out);
+    delete st;
+    return VOF_OK;
+}
+
+extern "C" int vof2d_streamer_create(const VofParams* p, int n_slabs, VofStreamer** out) {
+    if (!out) return fail(VOF_EINVAL, "null out pointer");
+    *out = nullptr;
+    if (!p) return fail(VOF_EINVAL, "null params");
+    if (p->slab_lo != 0 || p->slab_hi != 0) return fail(VOF_EINVAL, "the streamer takes full-domain params (slab_lo = slab_hi = 0)");
+    const int H = std::max(p->halo, p->n_jacobi + 3);
+    if (n_slabs < 1 || (n_slabs > 1 && p->nx / n_slabs < H))
+        return fail(VOF_EINVAL, "%d slabs of a %d-row domain are thinner than the halo %d", n_slabs, p->nx, H);
+    VofStreamer* st = new VofStreamer;
+    st->nx = p->nx; st->ny = p->ny; st->H = H;
+    int rc = VOF_OK;
+    for (int s = 0; s < n_slabs && rc == VOF_OK; ++s) {
+        VofParams q = *p;
+        q.slab_lo = 1 + (int)((long long)p->nx * s / n_slabs);
+        q.slab_hi = (int)((long long)p->nx * (s + 1) / n_slabs);
+        q.halo = n_slabs > 1 ? H : std::max(p->halo, 1);
+        VofCtx* c = nullptr;
+        rc = vof2d_create(&q, &c);
+        if (rc == VOF_OK) { st->slab.push_back(c); st->device = c->device; }
+    }
+    if (rc != VOF_OK) { vof2d_streamer_destroy(st); return rc; }
+    cudaError_t e = cudaSetDevice(st->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st->s_run, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st->s_out, cudaStreamNonBlocking);
+    st->ev_in.resize(n_slabs, nullptr); st->ev_run.resize(n_slabs, nullptr);
+    for (int s = 0; s < n_slabs && e == cudaSuccess; ++s) {
+        e = cudaEventCreateWithFlags(&st->ev_in[s], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&st->ev_run[s], cudaEventDisableTiming);
+    }
+    for (size_t s = 0; s < st->slab.size() && e == cudaSuccess; ++s)
+        if (vof2d_set_stream(st->slab[s], st->s_run) != VOF_OK) e = cudaErrorUnknown;
+    if (e != cudaSuccess) { vof2d_streamer_destroy(st); return fail((int)e, "streamer setup failed: %s", cudaGetErrorString(e)); }
+    *out = st;
+    return VOF_OK;
+}
+
+extern "C" int vof2d_streamer_info(const VofStreamer* st, int* n_slabs, int* halo, size_t* device_bytes) {
+    if (!st) return fail(VOF_EINVAL, "null streamer");
+    if (n_slabs) *n_slabs = (int)st->slab.size();
+    if (halo) *halo = st->H;
+    if (device_bytes) { size_t b = 0; for (VofCtx* c : st->slab) b += c->arena_bytes; *device_bytes = b; }
+    return VOF_OK;
+}
+
+// rows [ga, gb] (global) of one field between the dense host array and slab c
+static int streamer_copy(VofCtx* c, int field, const float* h_src, float* h_dst, int ga, int gb, cudaStream_t s) {
+    const size_t w = (size_t)(c->g.ny + 2) * sizeof(float), dp = (size_t)c->g.pitch * sizeof(float);
+    float* d = field_dev(c, field) + (size_t)(ga - c->g.gi0) * c->g.pitch;
+    if (h_src) CU(cudaMemcpy2DAsync(d, dp, h_src + (size_t)ga * (c->g.ny + 2), w, w, gb - ga + 1, cudaMemcpyHostToDevice, s));
+    if (h_dst) CU(cudaMemcpy2DAsync(h_dst + (size_t)ga * (c->g.ny + 2), w, d, dp, w, gb - ga + 1, cudaMemcpyDeviceToHost, s));
+    return VOF_OK;
+}
+
+extern "C" int vof2d_streamer_step_host(VofStreamer* st, int istep, unsigned flags, const float* u_in,
+                                        const float* v_in, const float* p_in, const float* F_in, float* u_out,
+                                        float* v_out, float* p_out, float* F_out) {
+    if (!st) return fail(VOF_EINVAL, "null streamer");
+    if (!u_in || !v_in || !p_in || !F_in || !u_out || !v_out || !p_out || !F_out)
+        return fail(VOF_EINVAL, "the streamed step needs all four input and all four output arrays");
+    CU(cudaSetDevice(st->device));
+    const int S = (int)st->slab.size();
+    const int ids[4] = {VOF_U, VOF_V, VOF_P, VOF_F};
+    const float* ins[4] = {u_in, v_in, p_in, F_in};
+    float* outs[4] = {u_out, v_out, p_out, F_out};
+    auto download = [&](int s) -> int {
+        VofCtx* c = st->slab[s];
+        CU(cudaStreamWaitEvent(st->s_out, st->ev_run[s], 0));
+        // in-place callers: slab s+1 reads my last H rows as its halo -- they may be overwritten only after that upload
+        if (s + 1 < S) CU(cudaStreamWaitEvent(st->s_out, st->ev_in[s + 1], 0));
+        const int ga = c->has_lo ? 0 : c->lo, gb = c->has_hi ? st->nx + 1 : c->hi;    // wall slabs own their ghost row
+        for (int k = 0; k < 4; ++k) TRY(streamer_copy(c, ids[k], nullptr, outs[k], ga, gb, st->s_out));
+        return VOF_OK;
+    };
+    for (int s = 0; s < S; ++s) {
+        VofCtx* c = st->slab[s];
+        const int ga = c->g.gi0 + c->all_a, gb = c->g.gi0 + c->all_b;
+        for (int k = 0; k < 4; ++k) TRY(streamer_copy(c, ids[k], ins[k], nullptr, ga, gb, st->s_in));
+        CU(cudaEventRecord(st->ev_in[s], st->s_in));
+        CU(cudaStreamWaitEvent(st->s_run, st->ev_in[s], 0));
+        TRY(step_impl(c, istep, flags));
+        CU(cudaEventRecord(st->ev_run[s], st->s_run));
+        if (s > 0) TRY(download(s - 1));
+    }
+    TRY(download(S - 1));
+    CU(cudaStreamSynchronize(st->s_out));
+    CU(cudaStreamSynchronize(st->s_run));
+    return VOF_OK;
+}

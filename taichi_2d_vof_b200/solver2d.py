@@ -289,3 +289,45 @@ class VofSolver2D:
 
     def halo_push(self, name, side, peer_dst):
         check(self._L.vof2d_halo_push(self._h, _lib.FIELD_IDS[name], side, C.c_void_p(peer_dst)))
+
+
+class VofStreamer2D:
+    """Host-resident state, device-streamed steps (include/vof.h: vof2d_streamer_*): the (nx+2, ny+2) arrays stay
+    in host memory and every step streams them through the GPU in ``n_slabs`` row slabs, upload / step / download
+    overlapped.  Results equal :meth:`VofSolver2D.step_host` bit for bit; use pinned arrays for the overlap."""
+
+    def __init__(self, params: VofParams | None = None, n_slabs: int = 16):
+        self._L = _lib.lib()
+        params = params if params is not None else reference_params()
+        self._h = C.c_void_p()
+        check(self._L.vof2d_streamer_create(C.byref(params), int(n_slabs), C.byref(self._h)))
+        n, h, b = C.c_int(), C.c_int(), C.c_size_t()
+        check(self._L.vof2d_streamer_info(self._h, C.byref(n), C.byref(h), C.byref(b)))
+        self.n_slabs, self.halo, self.device_bytes = n.value, h.value, b.value
+        self.nx, self.ny = params.nx, params.ny
+        self.istep = 0
+
+    def step_host(self, u, v, p, F, out=None, materialize_props=False):
+        """One step of the host-resident state; ``out`` = 4 preallocated arrays (default: in place)."""
+        self.istep += 1
+        out = out or (u, v, p, F)
+        shape = (self.nx + 2, self.ny + 2)
+        for a in (u, v, p, F) + tuple(out):
+            if a.shape != shape or a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"streamed step needs C-contiguous float32 arrays of shape {shape}")
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        flags = _lib.VOF_STEP_MATERIALIZE_PROPS if materialize_props else 0
+        check(self._L.vof2d_streamer_step_host(self._h, self.istep, flags, ptr(u), ptr(v), ptr(p), ptr(F),
+                                               ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3])))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.vof2d_streamer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -23,6 +23,11 @@ def _solver(P, **kw):
     return VofSolver2D(reference_params(nx=P.nx, ny=P.ny, Lx=P.Lx, Ly=P.Ly, n_jacobi=P.n_jacobi, **kw))
 
 
+def _params(P, **kw):
+    from taichi_2d_vof_b200 import reference_params
+    return reference_params(nx=P.nx, ny=P.ny, Lx=P.Lx, Ly=P.Ly, n_jacobi=P.n_jacobi, **kw)
+
+
 def _compare(s, o, fields, tol, exact=True, tag=""):
     for k in fields:
         a, b = getattr(s, k).to_numpy(), getattr(o, k)
@@ -113,6 +118,57 @@ def test_step_host_roundtrip(built_lib):
         s.step_host(u, v, p, F)
     for a, k in ((u, "u"), (v, "v"), (p, "p"), (F, "F")):
         assert np.array_equal(a, getattr(o, k)), k
+
+
+@pytest.mark.parametrize("nx,ny,n_slabs,inplace", [(96, 80, 3, True), (96, 80, 6, False), (200, 200, 4, True),
+                                                    (333, 130, 5, True), (64, 64, 1, True)])
+def test_streamed_step_host(built_lib, nx, ny, n_slabs, inplace):
+    """vof2d_streamer_step_host (row slabs streamed through the GPU, host-resident state) == oracle, bit for bit."""
+    from taichi_2d_vof_b200 import VofStreamer2D
+    P = Vof2DParams(nx=nx, ny=ny, Lx=0.0005 * nx, Ly=0.0005 * ny)
+    o = Vof2DOracle(P); o.set_init_F(3)
+    st = VofStreamer2D(_params(P), n_slabs=n_slabs)
+    assert st.n_slabs == n_slabs and (n_slabs == 1 or st.halo >= P.n_jacobi + 3)
+    a = [getattr(o, k).copy() for k in ("u", "v", "p", "F")]
+    b = [np.empty_like(x) for x in a]
+    for step in range(6):
+        o.step()
+        if inplace:
+            st.step_host(*a)
+        else:
+            st.step_host(*a, out=b)
+            a, b = b, a
+        for x, k in zip(a, ("u", "v", "p", "F")):
+            assert np.array_equal(x, getattr(o, k)), (k, step)
+    st.close()
+
+
+def test_streamed_step_host_random_state(built_lib):
+    """Streamed vs whole-array host step on random fields (every slab boundary carries non-trivial data)."""
+    from taichi_2d_vof_b200 import VofStreamer2D
+    rng = np.random.default_rng(5)
+    P = Vof2DParams(nx=260, ny=150, Lx=0.13, Ly=0.075)
+    shape = (P.nx + 2, P.ny + 2)
+    a = [(rng.random(shape, dtype=np.float32) - 0.5) * sc for sc in (2.0, 2.0, 100.0)] + [rng.random(shape, dtype=np.float32)]
+    b = [x.copy() for x in a]
+    s = _solver(P)
+    st = VofStreamer2D(_params(P), n_slabs=7)
+    for step in range(3):
+        s.step_host(*a)
+        st.step_host(*b)
+        for x, y, k in zip(a, b, ("u", "v", "p", "F")):
+            assert np.array_equal(x, y), (k, step)
+
+
+def test_streamer_argument_errors(built_lib):
+    from taichi_2d_vof_b200 import VofError, VofStreamer2D
+    P = Vof2DParams(nx=64, ny=64)
+    with pytest.raises(VofError):
+        VofStreamer2D(_params(P), n_slabs=8)        # 8-row slabs are thinner than the halo
+    st = VofStreamer2D(_params(P), n_slabs=2)
+    bad = np.zeros((10, 10), np.float32)
+    with pytest.raises(ValueError):
+        st.step_host(bad, bad, bad, bad)
 
 
 def test_random_state_one_step(built_lib):
