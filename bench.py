@@ -320,10 +320,10 @@ def run_ours(args):
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only), bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = time_cpu_port(n if n <= 8192 else 8192, 3, 1)
+        r = time_cpu_port(n if n <= 8192 else 8192, 24, 1)
         cpu = {"value": r["gcell_updates_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                "timesteps_per_s": r["steps_per_s"],
-               "sample": f"3 steps (+1 warm-up) of the same -ic 3 workload at {r['n']}^2, C/OpenMP restatement of 2dvof.py with the "
+               "sample": f"24 steps (+1 warm-up) of the same -ic 3 workload at {r['n']}^2, C/OpenMP restatement of 2dvof.py with the "
                          f"reference's loop structure, {r['threads']} threads ({r['seconds']:.1f} s)"}
 
     if rank == 0:
