@@ -21,6 +21,8 @@ KERNEL_KINDS = ("props", "kappa", "advect", "bc", "rhs", "jacobi", "project", "f
 VOF_OPT_JACOBI_TB = 0
 VOF_OPT_FCT_X_COLS = 1
 VOF_OPT_ADVECT_COLS = 2
+VOF_OPT_ADAPTIVE = 3
+VOF_OPT_CHUNK_CAP = 4
 VOF_STEP_MATERIALIZE_PROPS = 1
 VOF_STEP_NO_FUSION = 2
 VOF_SLAB_MIN_HALO = 13

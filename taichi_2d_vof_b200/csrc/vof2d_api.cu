@@ -71,6 +71,9 @@ struct VofCtx {
     int opt_jacobi_tb;         // 1: temporal blocking (default), 0: one launch per sweep
     int opt_fct_x_cols;        // columns per lane of the x-sweep (2 or 4)
     int opt_advect_cols;       // columns per lane of the momentum predictor (2 or 4)
+    int resident[8];           // resident blocks (whole device) of the persistent streaming kernels, by variant; 0 = not asked yet
+    int opt_chunk_cap;         // > 0: upper bound on the rows one warp marches in the streaming kernels (load-balance experiments)
+    int opt_adaptive;          // 1: interface-adaptive kernels (warp-uniform bulk rows short-cut, cp.async ring), 0: first generation
     char* peer_arena[2];       // neighbour arenas mapped into this process (lower / upper), NVLink P2P
     long long peer_nrows[2];
     bool peer_ipc[2];
@@ -207,6 +210,8 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     c->opt_jacobi_tb = 1;
     c->opt_fct_x_cols = 2;
     c->opt_advect_cols = 2;
+    c->opt_adaptive = 1;
+    c->opt_chunk_cap = 0;
     c->sm_count = prop.multiProcessorCount;
     c->all_a = std::max(0, -g.gi0);
     c->all_b = std::min(g.nrows - 1, P.nx + 1 - g.gi0);
@@ -340,7 +345,24 @@ static int chunk_rows(const VofCtx* c, int rows, int columns_of_units, int min_r
     int r = cdiv(rows, nch);
     r = std::max(r, min_rows);
     r = std::min(r, max_rows);
+    if (c->opt_chunk_cap > 0) r = std::min(r, c->opt_chunk_cap);
     return std::max(1, std::min(r, rows));
+}
+
+// persistent launch: blocks that are resident at once (asked once per kernel variant)
+template <typename K>
+static int resident_blocks(VofCtx* c, K kern, int threads, int slot) {
+    if (!c->resident[slot]) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, 0) != cudaSuccess) nb = 1;
+        c->resident[slot] = std::max(1, nb) * c->sm_count;
+    }
+    return c->resident[slot];
+}
+template <typename K, typename... Args>
+static void launch_queue(VofCtx* c, K kern, int slot, int warps_per_block, int nitems, Args... args) {
+    const int blocks = std::min(cdiv(nitems, warps_per_block), resident_blocks(c, kern, 32 * warps_per_block, slot));
+    kern<<<blocks, 32 * warps_per_block, 0, c->stream>>>(args...);
 }
 
 static unsigned bc_mask_all = 31u;
@@ -368,9 +390,14 @@ static int run_kappa(VofCtx* c) {
     Span span_(c, VOF_K_KAPPA);
     const int rows = c->in_b - c->in_a + 1;
     const int nstrips = cdiv(c->g.ny, kKapValid);
-    const int rpc = chunk_rows(c, rows, nstrips, 16, 64);
+    // adaptive kernel: items come from a queue and bulk rows are nearly free, so short items (less tail behind the
+    // few expensive interface items) cost little; first generation: long chunks amortise the 4 warm-up rows
+    const int rpc = c->opt_adaptive ? chunk_rows(c, rows, nstrips, 16, 24) : chunk_rows(c, rows, nstrips, 16, 64);
     dim3 grid(cdiv(nstrips * cdiv(rows, rpc), kKapWarps));
-    k_kappa4<<<grid, 32 * kKapWarps, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_KAPPA], c->in_a, c->in_b, rpc, nstrips);
+    if (c->opt_adaptive) {
+        const int nitems = nstrips * cdiv(rows, rpc);
+        launch_queue(c, k_kappa5, 4, kKapWarps, nitems, c->g, c->k, WorkQueue{c->diag->wq, nitems}, c->F(), c->buf[BUF_KAPPA], c->in_a, c->in_b, rpc, nstrips);
+    } else k_kappa4<false><<<grid, 32 * kKapWarps, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[BUF_KAPPA], c->in_a, c->in_b, rpc, nstrips);
     return launch_ok("k_kappa4");
 }
 
@@ -511,11 +538,23 @@ static int run_fct_x(VofCtx* c, bool post) {
     const int rows = c->in_b - c->in_a + 1;
     const int nc = c->opt_fct_x_cols;
     const int nstrips = cdiv(c->g.ny + 1, 32 * nc);
-    const int rpc = chunk_rows(c, rows, nstrips, 24, 96);     // 6 warm-up rows are re-read per chunk
+    const int rpc = c->opt_adaptive ? chunk_rows(c, rows, nstrips, 24, 48)      // queue-scheduled: shorter items, less tail
+                                    : chunk_rows(c, rows, nstrips, 24, 96);     // 6 warm-up rows are re-read per chunk
     const int nwarps = nstrips * cdiv(rows, rpc);
     dim3 grid(cdiv(nwarps, kFctXWarps));
 #define FXA c->g, c->fctx, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, rpc, nstrips
-    if (nc == 2) {
+    if (c->opt_adaptive) {
+        WorkQueue wq{c->diag->wq, nwarps};
+#define FXQ c->g, c->fctx, wq, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, rpc, nstrips
+        if (nc == 2) {
+            if (post) launch_queue(c, k_fct_x5<true, 2>, 0, kFctXWarps, nwarps, FXQ);
+            else launch_queue(c, k_fct_x5<false, 2>, 1, kFctXWarps, nwarps, FXQ);
+        } else {
+            if (post) launch_queue(c, k_fct_x5<true, 4>, 2, kFctXWarps, nwarps, FXQ);
+            else launch_queue(c, k_fct_x5<false, 4>, 3, kFctXWarps, nwarps, FXQ);
+        }
+#undef FXQ
+    } else if (nc == 2) {
         if (post) k_fct_x4<true, 2><<<grid, 32 * kFctXWarps, 0, c->stream>>>(FXA);
         else k_fct_x4<false, 2><<<grid, 32 * kFctXWarps, 0, c->stream>>>(FXA);
     } else {
@@ -534,8 +573,16 @@ static int run_fct_y(VofCtx* c, bool post) {
     const int rpw = chunk_rows(c, rows, nstrips, 2, 16);
     const int nwarps = nstrips * cdiv(rows, rpw);
     dim3 grid(cdiv(nwarps, kFctYWarps));
-    if (post) k_fct_y4<true><<<grid, 32 * kFctYWarps, 0, c->stream>>>(c->g, c->fcty, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b, rpw, nstrips);
-    else k_fct_y4<false><<<grid, 32 * kFctYWarps, 0, c->stream>>>(c->g, c->fcty, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b, rpw, nstrips);
+#define FYA c->g, c->fcty, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b, rpw, nstrips
+    if (c->opt_adaptive) {
+        WorkQueue wq{c->diag->wq, nwarps};
+        if (post) launch_queue(c, k_fct_y5<true>, 5, kFctYWarps, nwarps, c->g, c->fcty, wq, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b, rpw, nstrips);
+        else launch_queue(c, k_fct_y5<false>, 6, kFctYWarps, nwarps, c->g, c->fcty, wq, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b, rpw, nstrips);
+    } else {
+        if (post) k_fct_y4<true, false><<<grid, 32 * kFctYWarps, 0, c->stream>>>(FYA);
+        else k_fct_y4<false, false><<<grid, 32 * kFctYWarps, 0, c->stream>>>(FYA);
+    }
+#undef FYA
     c->F_cur ^= 1;
     return launch_ok("k_fct_y4");
 }
@@ -894,6 +941,8 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
     switch (option) {
         case VOF_OPT_JACOBI_TB: if (value < 0 || value > 2) return fail(VOF_EINVAL, "jacobi_tb must be 0, 1 or 2"); c->opt_jacobi_tb = value; break;
         case VOF_OPT_ADVECT_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "advect columns per lane must be 2 or 4"); c->opt_advect_cols = value; break;
+        case VOF_OPT_CHUNK_CAP: if (value < 0) return fail(VOF_EINVAL, "chunk cap must be >= 0"); c->opt_chunk_cap = value; break;
+        case VOF_OPT_ADAPTIVE: if (value != 0 && value != 1) return fail(VOF_EINVAL, "adaptive must be 0 or 1"); c->opt_adaptive = value; break;
         case VOF_OPT_FCT_X_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "fct_x columns per lane must be 2 or 4"); c->opt_fct_x_cols = value; break;
         default: return fail(VOF_EINVAL, "unknown option %d", option);
     }

@@ -16,6 +16,7 @@
 // exchanges the radius-3 chain with its neighbour lanes by shuffles (120 of 128 columns are stored).
 #pragma once
 #include "vof2d_jacobi_tb.cuh"
+#include "vof2d_stream.cuh"
 #include "vof_common.cuh"
 
 namespace vof {
@@ -46,6 +47,27 @@ __device__ __forceinline__ float fct_ftd2(float F_c, float lo_c, float lo_p, flo
     if (s != 0.0f) t = F_c + fdiv_const(s * c.dy, c.d_dxdy, c.fast_div_ok);   // F + (+-0) = F otherwise
     float r = 0.0f;
     if (t != 0.0f) {                                   // 0 * dx * dy / dv = 0
+        r = ((t * c.dx) * c.dy) / dv;
+        if (r > 1.0f || r < 0.0f) r = var01(r);
+    }
+    return interior ? r : 0.0f;
+}
+
+// The same with one more exact short-cut: a full cell (t == 1) whose faces move alike (dv == dx*dy bit for bit -- the
+// liquid at rest, or in uniform motion) evaluates ((1 * dx) * dy) / (dx*dy), a constant: `td_one` is that expression,
+// range check included, evaluated once per work item by the same instructions.
+__device__ __forceinline__ float fct_td_one(const FctC& c) {
+    float r = ((1.0f * c.dx) * c.dy) / c.dxdy;
+    if (r > 1.0f || r < 0.0f) r = var01(r);
+    return r;
+}
+__device__ __forceinline__ float fct_ftd3(float F_c, float lo_c, float lo_p, float dv, bool interior, const FctC& c, float td_one) {
+    const float s = lo_c - lo_p;
+    float t = F_c;
+    if (s != 0.0f) t = F_c + fdiv_const(s * c.dy, c.d_dxdy, c.fast_div_ok);   // F + (+-0) = F otherwise
+    float r = 0.0f;
+    if (t == 1.0f && dv == c.dxdy) r = td_one;
+    else if (t != 0.0f) {                              // 0 * dx * dy / dv = 0
         r = ((t * c.dx) * c.dy) / dv;
         if (r > 1.0f || r < 0.0f) r = var01(r);
     }
@@ -184,13 +206,174 @@ k_fct_x4(Grid g, FctC c, const float* __restrict__ Fin, const float* __restrict_
     }
 }
 
+// --------------------------------------------------------------------------------------
+// x-sweep, second generation: the same per-cell arithmetic (fct_face .. fct_update2), fed by the per-lane cp.async
+// ring of vof2d_stream.cuh, scheduled through a work queue, with two warp-uniform short-cuts for the bulk of a
+// two-phase field.
+//   * Gas mode: while the 7 rows F[k-6 .. k] of the strip are all 0 (and u finite), cell k-3 stays 0: 0 * dx * dy
+//     / dv = 0, all fluxes +-0.  The pipeline is not advanced; when a non-zero row arrives its state is what 7
+//     zero rows leave behind: Ftd = 0, a = 0, ratios 0, lo = (u dt) * 0 -- the chunk's initial state.
+//   * Flux-free rows (any uniform value, typically the liquid at exactly 1): when no lane has a non-zero
+//     antidiffusive flux on faces k-3 .. k-1, ratios, face limiter and corrective update are skipped warp-wide
+//     instead of lane by lane (no divergence bookkeeping): F' = var(Ftd).
+// --------------------------------------------------------------------------------------
+constexpr int kFctXSlots = 8;                  // ring slots per lane and field (6 rows in flight)
+
+template <bool POST, int NC>
+__global__ void __launch_bounds__(32 * kFctXWarps)
+k_fct_x5(Grid g, FctC c, WorkQueue wq, const float* __restrict__ Fin, const float* __restrict__ u, float* __restrict__ Fout,
+         int r0, int r1, int rows_per_chunk, int nstrips) {
+    using Ring = RowRing<2, NC, kFctXSlots, 32 * kFctXWarps>;
+    __shared__ __align__(16) unsigned char ring_mem[Ring::kBytes];
+    const int lane = threadIdx.x & 31;
+    const int P = g.pitch, last = g.nrows - 1;
+    const long long P4 = (long long)P * 4;
+    const float td_one = fct_td_one(c);
+    Ring ring;
+    ring.init(ring_mem, threadIdx.x);
+    for (;;) {
+    const int item = wq_claim(wq, lane);
+    if (item >= wq.nitems) break;
+    const int strip = item % nstrips, chunk = item / nstrips;
+    const int ia = r0 + chunk * rows_per_chunk;
+    const int ib = min(r1, ia + rows_per_chunk - 1);
+    const int jl = 1 + 32 * NC * strip + NC * lane;
+    const bool active = jl <= g.ny + 1;                                 // idle lanes stay for the votes
+    const float* Fc = Fin + jl;
+    const float* uc = u + jl;
+    char* Fo = reinterpret_cast<char*>(Fout + jl);
+    const float* const src[2] = {Fc, uc};
+    auto ldv = [&](const float* base, int i, float (&x)[NC]) { VecN<NC>::ld(base + (size_t)min(max(i, 0), last) * P, x); };
+    const bool lo_wall = g.gi0 + ia == 1, hi_wall = g.gi0 + ib == g.nx;
+    // ghost rows / ghost column 0 pass through (the sweep never writes them; out-of-place needs the copy)
+    if (active && lo_wall) { float t[NC]; ldv(Fc, ia - 1, t); VecN<NC>::st(reinterpret_cast<float*>(Fo + (ia - 1) * P4), t); }
+    if (active && hi_wall) { float t[NC]; ldv(Fc, ib + 1, t); VecN<NC>::st(reinterpret_cast<float*>(Fo + (ib + 1) * P4), t); }
+    if (strip == 0 && lane == 0) {
+        for (int i = ia - (lo_wall ? 1 : 0); i <= ib + (hi_wall ? 1 : 0); ++i) Fout[(size_t)i * P] = Fin[(size_t)i * P];
+    }
+    bool colin[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) colin[k] = jl + k <= g.ny;
+    const bool ragged = __any_sync(0xffffffffu, active && !colin[NC - 1]);   // only the last strip has columns past ny
+
+    ring.start(active, ia - 3, ib + 3, last, P, src);
+    float X[2][NC];
+    float F1[NC], u1[NC], lo1[NC], a1[NC], a2[NC], a3[NC], td1[NC], td2[NC], td3[NC], dv1[NC], dv2[NC], dv3[NC], rp2[NC], rm2[NC], c2[NC];
+    ring.next(X, src);                                                  // row ia-3
+#pragma unroll
+    for (int q = 0; q < NC; ++q) { F1[q] = X[0][q]; u1[q] = X[1][q]; }
+    auto reset_state = [&]() {          // what 7 all-zero rows leave in the pipeline (= the start of a chunk)
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+            lo1[q] = (u1[q] * c.dt) * 0.0f;
+            a1[q] = a2[q] = a3[q] = 0.f; td1[q] = td2[q] = td3[q] = 0.f;
+            dv1[q] = dv2[q] = dv3[q] = 1.f; rp2[q] = rm2[q] = 0.f; c2[q] = 0.f;
+        }
+    };
+    reset_state();
+    // zbits: bit b = row k-b of the strip is all zero with finite u.  Rows before ia-3 count as zero: no stored cell
+    // depends on them (radius 3), and the pipeline's initial state above is the state zero rows leave behind.
+    // abits: bit b = some lane has a non-zero antidiffusive flux on face k-b
+    unsigned zbits, abits = 0;
+    {
+        bool z = all_finite_n<NC>(u1);
+#pragma unroll
+        for (int q = 0; q < NC; ++q) z = z && F1[q] == 0.0f;
+        zbits = 0xfffffffeu | (__all_sync(0xffffffffu, z) ? 1u : 0u);
+    }
+    bool gas = true;                                                    // state == reset_state()
+    for (int k = ia - 2; k <= ib + 3; ++k) {
+        ring.next(X, src);                                              // row k
+        const float (&Fk)[NC] = X[0];
+        const float (&uk)[NC] = X[1];
+        const int io = k - 3;
+        const bool store = active && io >= ia;                          // io <= ib by the loop bound; rows ia..ib are interior
+        float out[NC];
+        bool z = all_finite_n<NC>(uk);
+#pragma unroll
+        for (int q = 0; q < NC; ++q) z = z && Fk[q] == 0.0f;
+        zbits = (zbits << 1) | (__all_sync(0xffffffffu, z) ? 1u : 0u);
+        if ((zbits & 0x7fu) == 0x7fu) {                                 // rows k-6 .. k are zero: cell k-3 stays zero
+            gas = true;
+#pragma unroll
+            for (int q = 0; q < NC; ++q) out[q] = 0.0f;
+        } else {
+            if (gas) { reset_state(); abits = 0; gas = false; }        // u1 = u[k-1]; F1 = row k-1
+            const int gk = g.gi0 + k;
+            const bool in1 = gk - 1 >= 1 && gk - 1 <= g.nx;             // cell k-1 interior
+            const bool in2 = gk - 2 >= 1 && gk - 2 <= g.nx;             // cell k-2 interior
+            const bool face2 = gk - 2 >= 2 && gk - 2 <= g.nx + 1;       // face k-2 has a limiter (cx[1] is never written)
+            float a0[NC];
+            bool anya = false;
+#pragma unroll
+            for (int q = 0; q < NC; ++q) {
+                float lo0;
+                fct_face(uk[q], F1[q], Fk[q], c, lo0, a0[q]);                                // face k
+                const float dv_n = c.dxdy - c.dtd * (uk[q] - u1[q]);                         // cell k-1
+                const float td_n = fct_ftd3(F1[q], lo1[q], lo0, dv_n, in1, c, td_one);
+                td3[q] = td2[q]; td2[q] = td1[q]; td1[q] = td_n;
+                dv3[q] = dv2[q]; dv2[q] = dv1[q]; dv1[q] = dv_n;
+                lo1[q] = lo0;
+                anya = anya || a0[q] != 0.0f;
+            }
+            abits = (abits << 1) | (__any_sync(0xffffffffu, anya) ? 1u : 0u);
+            if ((abits & 0xeu) == 0u) {                                 // faces k-1, k-2, k-3 carry no flux in any lane
+#pragma unroll
+                for (int q = 0; q < NC; ++q) {
+                    float f = var01(td3[q]);
+                    if (POST) f = var01(f);
+                    out[q] = f;
+                    rp2[q] = 0.0f; rm2[q] = 0.0f; c2[q] = 0.0f;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < NC; ++q) {
+                    float rp_n, rm_n;
+                    fct_ratios2(td3[q], td2[q], td1[q], a2[q], a1[q], in2, c, rp_n, rm_n);       // cell k-2
+                    const float c_n = fct_cface2(a2[q], rp2[q], rm2[q], rp_n, rm_n, face2);      // face k-2
+                    out[q] = fct_update2<POST>(td3[q], a3[q], c2[q], a2[q], c_n, dv3[q], c);     // cell k-3
+                    rp2[q] = rp_n; rm2[q] = rm_n; c2[q] = c_n;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NC; ++q) { a3[q] = a2[q]; a2[q] = a1[q]; a1[q] = a0[q]; }
+        }
+        if (store) {
+            if (ragged && !colin[NC - 1]) {       // pass-through for columns past ny (ghost ny+1, padding)
+                float old[NC];
+                ldv(Fc, io, old);
+#pragma unroll
+                for (int q = 0; q < NC; ++q) out[q] = colin[q] ? out[q] : old[q];
+            }
+            VecN<NC>::st(reinterpret_cast<float*>(Fo + io * P4), out);
+        }
+#pragma unroll
+        for (int q = 0; q < NC; ++q) { F1[q] = Fk[q]; u1[q] = uk[q]; }
+    }
+    }
+    ring.drain();
+    wq_leave(wq, lane, gridDim.x * kFctXWarps);
+}
+
 // ======================================================================================
 // y-sweep: warp = strip of 128 columns (lanes 1..30 store), one row per iteration
 // ======================================================================================
 constexpr int kFctYWarps = 4;
 constexpr int kFctYValid = 120;
 
-template <bool POST>
+// every bit pattern with an all-ones exponent is inf or NaN
+__device__ __forceinline__ bool all_finite4(const float (&x)[4]) {
+    const unsigned m = 0x7fffffffu;
+    const unsigned a = max(max(__float_as_uint(x[0]) & m, __float_as_uint(x[1]) & m),
+                           max(__float_as_uint(x[2]) & m, __float_as_uint(x[3]) & m));
+    return a < 0x7f800000u;
+}
+
+// ADAPT: warp-uniform bulk rows.  A two-phase field is exactly 0 or exactly 1 away from the interface; when every
+// cell a warp's strip touches holds the same value c, every face has Fl == Fh == c, so its antidiffusive flux is
+// vd*c - vd*c = +0 (finite vd) and limiter, face limiter and corrective update are no-ops: F' = var(Ftd).  For c = 0
+// also Ftd = 0 (0 * dx * dy / dv), so the row is 0.  The test costs five compares and one vote per lane and row.
+template <bool POST, bool ADAPT>
 __global__ void __launch_bounds__(32 * kFctYWarps)
 k_fct_y4(Grid g, FctC c, const float* __restrict__ Fin, const float* __restrict__ v, float* __restrict__ Fout,
          int r0, int r1, int rows_per_warp, int nstrips) {
@@ -214,19 +397,64 @@ k_fct_y4(Grid g, FctC c, const float* __restrict__ Fin, const float* __restrict_
     bool fvalid[5];   // faces jl .. jl+4 carry a limiter (cy on face 1 is never written)
 #pragma unroll
     for (int k = 0; k < 5; ++k) fvalid[k] = jl + k >= 2 && jl + k <= g.ny + 1;
+    bool rel[4];      // columns that exist (ghosts included); padding is exempt from the uniformity test
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rel[k] = active && jl + k >= 0 && jl + k <= g.ny + 1;
 
-    float4 Fq = active ? *reinterpret_cast<const float4*>(Fc + (size_t)ia * P) : zero4;
-    float4 vq = active ? *reinterpret_cast<const float4*>(vc + (size_t)ia * P) : zero4;
-    for (int i = ia; i <= ib; ++i) {
-        const float F[4] = {Fq.x, Fq.y, Fq.z, Fq.w}, vv[4] = {vq.x, vq.y, vq.z, vq.w};
-        if (i < ib && active) {                                        // prefetch the next row
-            Fq = *reinterpret_cast<const float4*>(Fc + (size_t)(i + 1) * P);
-            vq = *reinterpret_cast<const float4*>(vc + (size_t)(i + 1) * P);
+    constexpr int PF = 2;                                              // rows in flight per warp
+    float4 Fq[PF], vq[PF];
+#pragma unroll
+    for (int d = 0; d < PF; ++d) {
+        const bool ok = active && ia + d <= ib;
+        Fq[d] = ok ? *reinterpret_cast<const float4*>(Fc + (size_t)(ia + d) * P) : zero4;
+        vq[d] = ok ? *reinterpret_cast<const float4*>(vc + (size_t)(ia + d) * P) : zero4;
+    }
+    for (int ibase = ia; ibase <= ib; ibase += PF) {
+#pragma unroll
+      for (int d = 0; d < PF; ++d) {
+        const int i = ibase + d;
+        if (i > ib) break;
+        const float F[4] = {Fq[d].x, Fq[d].y, Fq[d].z, Fq[d].w}, vv[4] = {vq[d].x, vq[d].y, vq[d].z, vq[d].w};
+        if (i + PF <= ib && active) {                                  // prefetch
+            Fq[d] = *reinterpret_cast<const float4*>(Fc + (size_t)(i + PF) * P);
+            vq[d] = *reinterpret_cast<const float4*>(vc + (size_t)(i + PF) * P);
         }
         const int gi = g.gi0 + i;
         const bool rowin = gi >= 1 && gi <= g.nx;
-        const float F_m1 = __shfl_up_sync(0xffffffffu, F[3], 1);       // F[jl-1]
         const float v_p4 = __shfl_down_sync(0xffffffffu, vv[0], 1);    // v[jl+4]
+        if (strip == 0 && lane == 0) Fout[(size_t)i * P] = F[3];       // ghost column 0 (jl + 3 == 0)
+        if (ADAPT) {
+            const float c0 = __shfl_sync(0xffffffffu, F[0], 1);        // lane 1's first column always exists
+            bool uni = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) uni = uni && (!rel[k] || F[k] == c0);
+            if (c0 == 0.0f) uni = uni && all_finite4(vv);              // 0 * inf must stay NaN: general path
+            if (__all_sync(0xffffffffu, uni)) {
+                if (store_lane) {
+                    float out[4];
+                    if (c0 == 0.0f) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) out[k] = (rowin && cin[k + 1]) ? 0.0f : F[k];
+                    } else {
+                        float lo[5];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) lo[k] = (vv[k] * c.dt) * c0;
+                        lo[4] = (v_p4 * c.dt) * c0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float dv = c.dxdy - c.dtd * ((k < 3 ? vv[k + 1] : v_p4) - vv[k]);
+                            const float td = fct_ftd2(F[k], lo[k], lo[k + 1], dv, cin[k + 1], c);
+                            float f = var01(td);
+                            if (POST) f = var01(f);
+                            out[k] = (rowin && cin[k + 1]) ? f : F[k];
+                        }
+                    }
+                    *reinterpret_cast<float4*>(Fo + (size_t)i * P) = make_float4(out[0], out[1], out[2], out[3]);
+                }
+                continue;
+            }
+        }
+        const float F_m1 = __shfl_up_sync(0xffffffffu, F[3], 1);       // F[jl-1]
         float lo[5], a[5];
 #pragma unroll
         for (int k = 0; k < 4; ++k) fct_face(vv[k], k ? F[k - 1] : F_m1, F[k], c, lo[k], a[k]);
@@ -258,8 +486,131 @@ k_fct_y4(Grid g, FctC c, const float* __restrict__ Fin, const float* __restrict_
             }
             *reinterpret_cast<float4*>(Fo + (size_t)i * P) = make_float4(out[0], out[1], out[2], out[3]);
         }
-        if (strip == 0 && lane == 0) Fout[(size_t)i * P] = F[3];       // ghost column 0 (jl + 3 == 0)
+      }
     }
 }
+
+// Second generation (ring + queue, vof2d_stream.cuh) -- ADAPT: warp-uniform bulk rows.  A two-phase field is exactly 0 or exactly 1 away from the interface; when every
+// cell a warp's strip touches holds the same value c, every face has Fl == Fh == c, so its antidiffusive flux is
+// vd*c - vd*c = +0 (finite vd) and limiter, face limiter and corrective update are no-ops: F' = var(Ftd).  For c = 0
+// also Ftd = 0 (0 * dx * dy / dv), so the row is 0.  The test costs five compares and one vote per lane and row.
+constexpr int kFctYSlots = 8;
+template <bool POST>
+__global__ void __launch_bounds__(32 * kFctYWarps)
+k_fct_y5(Grid g, FctC c, WorkQueue wq, const float* __restrict__ Fin, const float* __restrict__ v, float* __restrict__ Fout,
+         int r0, int r1, int rows_per_warp, int nstrips) {
+    constexpr bool ADAPT = true;
+    using Ring = RowRing<2, 4, kFctYSlots, 32 * kFctYWarps>;
+    __shared__ __align__(16) unsigned char ring_mem[Ring::kBytes];
+    const int lane = threadIdx.x & 31;
+    const float td_one = fct_td_one(c);
+    Ring ring;
+    ring.init(ring_mem, threadIdx.x);
+    for (;;) {
+    const int item = wq_claim(wq, lane);
+    if (item >= wq.nitems) break;
+    const int strip = item % nstrips, chunk = item / nstrips;
+    const int ia = r0 + chunk * rows_per_warp;
+    const int ib = min(r1, ia + rows_per_warp - 1);
+    const int jl = 1 - 4 + kFctYValid * strip + 4 * lane;     // == 1 (mod 4)
+    const bool active = jl <= g.ny + 1;
+    const bool store_lane = active && lane >= 1 && lane <= 30;
+    const int P = g.pitch;
+    const float* Fc = Fin + jl;
+    const float* vc = v + jl;
+    float* Fo = Fout + jl;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool cin[6];      // cells jl-1 .. jl+4 in the global interior
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cin[k] = jl - 1 + k >= 1 && jl - 1 + k <= g.ny;
+    bool fvalid[5];   // faces jl .. jl+4 carry a limiter (cy on face 1 is never written)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) fvalid[k] = jl + k >= 2 && jl + k <= g.ny + 1;
+    bool rel[4];      // columns that exist (ghosts included); padding is exempt from the uniformity test
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rel[k] = active && jl + k >= 0 && jl + k <= g.ny + 1;
+
+    const float* const src[2] = {Fc, vc};
+    ring.start(active, ia, ib, g.nrows - 1, P, src);
+    {
+      for (int i = ia; i <= ib; ++i) {
+        float X[2][4];
+        ring.next(X, src);
+        const float (&F)[4] = X[0];
+        const float (&vv)[4] = X[1];
+        const int gi = g.gi0 + i;
+        const bool rowin = gi >= 1 && gi <= g.nx;
+        const float v_p4 = __shfl_down_sync(0xffffffffu, vv[0], 1);    // v[jl+4]
+        if (strip == 0 && lane == 0) Fout[(size_t)i * P] = F[3];       // ghost column 0 (jl + 3 == 0)
+        if (ADAPT) {
+            const float c0 = __shfl_sync(0xffffffffu, F[0], 1);        // lane 1's first column always exists
+            bool uni = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) uni = uni && (!rel[k] || F[k] == c0);
+            if (c0 == 0.0f) uni = uni && all_finite4(vv);              // 0 * inf must stay NaN: general path
+            if (__all_sync(0xffffffffu, uni)) {
+                if (store_lane) {
+                    float out[4];
+                    if (c0 == 0.0f) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) out[k] = (rowin && cin[k + 1]) ? 0.0f : F[k];
+                    } else {
+                        float lo[5];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) lo[k] = (vv[k] * c.dt) * c0;
+                        lo[4] = (v_p4 * c.dt) * c0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float dv = c.dxdy - c.dtd * ((k < 3 ? vv[k + 1] : v_p4) - vv[k]);
+                            const float td = fct_ftd3(F[k], lo[k], lo[k + 1], dv, cin[k + 1], c, td_one);
+                            float f = var01(td);
+                            if (POST) f = var01(f);
+                            out[k] = (rowin && cin[k + 1]) ? f : F[k];
+                        }
+                    }
+                    *reinterpret_cast<float4*>(Fo + (size_t)i * P) = make_float4(out[0], out[1], out[2], out[3]);
+                }
+                continue;
+            }
+        }
+        const float F_m1 = __shfl_up_sync(0xffffffffu, F[3], 1);       // F[jl-1]
+        float lo[5], a[5];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fct_face(vv[k], k ? F[k - 1] : F_m1, F[k], c, lo[k], a[k]);
+        lo[4] = __shfl_down_sync(0xffffffffu, lo[0], 1);
+        a[4] = __shfl_down_sync(0xffffffffu, a[0], 1);
+        float dv[4], td[6];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            dv[k] = c.dxdy - c.dtd * ((k < 3 ? vv[k + 1] : v_p4) - vv[k]);
+            td[k + 1] = fct_ftd3(F[k], lo[k], lo[k + 1], dv[k], cin[k + 1], c, td_one);
+        }
+        td[0] = __shfl_up_sync(0xffffffffu, td[4], 1);
+        td[5] = __shfl_down_sync(0xffffffffu, td[1], 1);
+        float rp[5], rm[5];   // index k+1 = cell jl+k; index 0 = cell jl-1
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fct_ratios2(td[k], td[k + 1], td[k + 2], a[k], a[k + 1], cin[k + 1], c, rp[k + 1], rm[k + 1]);
+        rp[0] = __shfl_up_sync(0xffffffffu, rp[4], 1);
+        rm[0] = __shfl_up_sync(0xffffffffu, rm[4], 1);
+        float cf[5];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cf[k] = fct_cface2(a[k], rp[k], rm[k], rp[k + 1], rm[k + 1], fvalid[k]);
+        cf[4] = __shfl_down_sync(0xffffffffu, cf[0], 1);
+        if (store_lane) {
+            float out[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float f = fct_update2<POST>(td[k + 1], a[k], cf[k], a[k + 1], cf[k + 1], dv[k], c);
+                out[k] = (rowin && cin[k + 1]) ? f : F[k];             // ghost rows / columns pass through
+            }
+            *reinterpret_cast<float4*>(Fo + (size_t)i * P) = make_float4(out[0], out[1], out[2], out[3]);
+        }
+      }
+    }
+    }
+    ring.drain();
+    wq_leave(wq, lane, gridDim.x * kFctYWarps);
+}
+
 
 }  // namespace vof

@@ -239,7 +239,8 @@ struct Diag {
     unsigned int max_cfl_bits;
     unsigned int resid_bits;
     unsigned long long courant_count;
-    unsigned int queue;          // work-queue head of the persistent kernels
+    unsigned int queue;          // work-queue head of the persistent Jacobi kernel (zeroed before each launch)
+    unsigned int wq[2];          // WorkQueue counters of the streaming kernels (self re-arming, vof2d_stream.cuh)
 };
 
 __global__ void __launch_bounds__(256)
