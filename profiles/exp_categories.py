@@ -48,7 +48,7 @@ for k in range(steps):
         classify(f"step {k + 1}")
 from taichi_2d_vof_b200 import _lib
 state = {k: getattr(s, k).to_numpy() for k in ("F", "u", "v")}
-MODES = ((1, 4), (1, 2), (0, 2))
+MODES = ((1, 2), (0, 2))
 for adaptive, cols in MODES:
     s.set_option(_lib.VOF_OPT_ADAPTIVE, adaptive); s.set_option(_lib.VOF_OPT_FCT_X_COLS, cols)
     print(f"timings on the -ic 3 state, adaptive={adaptive} fct_x cols={cols}:")

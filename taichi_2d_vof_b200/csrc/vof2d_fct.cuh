@@ -227,7 +227,8 @@ k_fct_x5(Grid g, FctC c, WorkQueue wq, const float* __restrict__ Fin, const floa
     __shared__ __align__(16) unsigned char ring_mem[Ring::kBytes];
     const int lane = threadIdx.x & 31;
     const int P = g.pitch, last = g.nrows - 1;
-    const long long P4 = (long long)P * 4;
+    const int P4i = P * 4;
+    const long long P4 = P4i;
     const float td_one = fct_td_one(c);
     Ring ring;
     ring.init(ring_mem, threadIdx.x);
@@ -254,7 +255,13 @@ k_fct_x5(Grid g, FctC c, WorkQueue wq, const float* __restrict__ Fin, const floa
     bool colin[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) colin[k] = jl + k <= g.ny;
-    const bool ragged = __any_sync(0xffffffffu, active && !colin[NC - 1]);   // only the last strip has columns past ny
+    if (active && !colin[NC - 1]) {               // last strip only: ghost column ny+1 and padding pass through
+        for (int i = ia; i <= ib; ++i) {
+#pragma unroll
+            for (int q = 0; q < NC; ++q) if (!colin[q]) Fout[(size_t)i * P + jl + q] = Fin[(size_t)i * P + jl + q];
+        }
+    }
+    char* po = Fo + (long long)ia * P4i;          // row io = ia is the first one stored
 
     ring.start(active, ia - 3, ib + 3, last, P, src);
     float X[2][NC];
@@ -339,14 +346,14 @@ k_fct_x5(Grid g, FctC c, WorkQueue wq, const float* __restrict__ Fin, const floa
             for (int q = 0; q < NC; ++q) { a3[q] = a2[q]; a2[q] = a1[q]; a1[q] = a0[q]; }
         }
         if (store) {
-            if (ragged && !colin[NC - 1]) {       // pass-through for columns past ny (ghost ny+1, padding)
-                float old[NC];
-                ldv(Fc, io, old);
+            float* dst = reinterpret_cast<float*>(po);
+            if (colin[NC - 1]) VecN<NC>::st(dst, out);
+            else {                                // last strip: columns past ny were copied through above
 #pragma unroll
-                for (int q = 0; q < NC; ++q) out[q] = colin[q] ? out[q] : old[q];
+                for (int q = 0; q < NC; ++q) if (colin[q]) dst[q] = out[q];
             }
-            VecN<NC>::st(reinterpret_cast<float*>(Fo + io * P4), out);
         }
+        if (io >= ia) po += P4;
 #pragma unroll
         for (int q = 0; q < NC; ++q) { F1[q] = Fk[q]; u1[q] = uk[q]; }
     }
