@@ -71,7 +71,7 @@ struct VofCtx {
     int opt_jacobi_tb;         // 1: temporal blocking (default), 0: one launch per sweep
     int opt_fct_x_cols;        // columns per lane of the x-sweep (2 or 4)
     int opt_advect_cols;       // columns per lane of the momentum predictor (2 or 4)
-    int resident[8];           // resident blocks (whole device) of the persistent streaming kernels, by variant; 0 = not asked yet
+    int resident[16];          // resident blocks (whole device) of the persistent streaming kernels, by variant; 0 = not asked yet
     int opt_chunk_cap;         // > 0: upper bound on the rows one warp marches in the streaming kernels (load-balance experiments)
     int opt_adaptive;          // 1: interface-adaptive kernels (warp-uniform bulk rows short-cut, cp.async ring), 0: first generation
     char* peer_arena[2];       // neighbour arenas mapped into this process (lower / upper), NVLink P2P
@@ -410,6 +410,14 @@ static int run_advect(VofCtx* c, bool inline_props) {
     const int nstrips = cdiv(c->g.ny, 32 * nc);
     const int rpc = chunk_rows(c, rows, nstrips, 8, 64);
     dim3 grid(cdiv(nstrips * cdiv(rows, rpc), kMomWarps));
+    if (c->opt_adaptive && inline_props && nc == 2) {
+        const int nitems = nstrips * cdiv(rows, rpc);
+        WorkQueue wq{c->diag->wq, nitems};
+#define ADQ c->g, c->mom, wq, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->buf[BUF_KAPPA], c->buf[BUF_US], c->buf[BUF_VS], a, b, rpc, nstrips
+        launch_queue(c, k_advect5<2>, 7, kMomWarps, nitems, ADQ);      // 4 columns per lane would need > 48 KB of ring
+#undef ADQ
+        return launch_ok("k_advect5");
+    }
 #define ADA c->g, c->mom, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->buf[BUF_KAPPA], c->buf[BUF_RHO], c->buf[BUF_NU], c->buf[BUF_US], c->buf[BUF_VS], a, b, rpc, nstrips
     if (nc == 2) {
         if (inline_props) k_advect4<true, 2><<<grid, 32 * kMomWarps, 0, c->stream>>>(ADA);

@@ -9,6 +9,7 @@
 #pragma once
 #include "vof2d_fct.cuh"
 #include "vof2d_jacobi_tb.cuh"
+#include "vof2d_stream.cuh"
 #include "vof_common.cuh"
 
 namespace vof {
@@ -179,6 +180,67 @@ k_advect4(Grid g, MomC c, const float* __restrict__ u, const float* __restrict__
         adv_load<INLINE_PROPS, NC, 2>(S, c, u, v, F, kappa, rho, nu, (size_t)min(i + 3, g.nrows - 1) * P + col, lane, active);
         if (active) adv_row<INLINE_PROPS, NC, 2>(S, c, rho, P, us, vs, (size_t)(i + 2) * P + col, g.gi0 + i + 2, jl, g.nx, g.ny);
     }
+}
+
+// --------------------------------------------------------------------------------------
+// Momentum predictor, second generation: the same adv_row arithmetic; rows of u, v, F, kappa (and the columns next to
+// the strip) arrive through the per-lane cp.async ring, items through the work queue (vof2d_stream.cuh).  The
+// first-generation kernel waited on global loads issued one row ahead (ncu: long-scoreboard stalls dominate).
+// Properties are always taken from F (the fused step); the materialised rho / nu variant stays k_advect4<false>.
+// --------------------------------------------------------------------------------------
+constexpr int kAdvSlots = 8;
+
+template <int NC, int PH, class Ring>
+__device__ __forceinline__ void adv_load_ring(AdvState<true, NC>& S, const MomC& c, Ring& ring, const float* const (&src)[4]) {
+    float X[4][NC + 2];
+    ring.next(X, src);
+#pragma unroll
+    for (int q = 0; q < NC + 2; ++q) { S.u[PH].x[q] = X[0][q]; S.v[PH].x[q] = X[1][q]; }
+#pragma unroll
+    for (int q = 0; q < NC + 1; ++q) { S.F[PH].x[q] = X[2][q]; S.kp[PH].x[q] = X[3][q]; }
+#pragma unroll
+    for (int q = 0; q < NC; ++q) S.nu[PH][q] = nu_of(S.F[PH].x[q + 1], c.k);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(32 * kMomWarps)
+k_advect5(Grid g, MomC c, WorkQueue wq, const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ F,
+          const float* __restrict__ kappa, float* __restrict__ us, float* __restrict__ vs, int r0, int r1, int rows_per_chunk,
+          int nstrips) {
+    using Ring = RowRingH<4, NC, kAdvSlots, 32 * kMomWarps, 0xfu, 0x3u>;     // left: u, v, F, kappa; right: u, v
+    __shared__ __align__(16) unsigned char ring_mem[Ring::kBytes];
+    const int lane = threadIdx.x & 31;
+    const int P = g.pitch;
+    Ring ring;
+    ring.init(ring_mem, threadIdx.x);
+    for (;;) {
+        const int item = wq_claim(wq, lane);
+        if (item >= wq.nitems) break;
+        const int strip = item % nstrips, chunk = item / nstrips;
+        const int ia = r0 + chunk * rows_per_chunk;
+        const int ib = min(r1, ia + rows_per_chunk - 1);
+        const int jl = 1 + 32 * NC * strip + NC * lane;
+        const bool active = jl <= g.ny + 1;
+        const size_t col = (size_t)jl;
+        const float* const src[4] = {u + jl, v + jl, F + jl, kappa + jl};
+        ring.start(active, ia - 1, ib + 1, g.nrows - 1, P, src);
+        AdvState<true, NC> S;
+        // rows ia-1 and ia enter slots 1 and 2 (OLD and MID of phase 0)
+        adv_load_ring<NC, 1>(S, c, ring, src);
+        adv_load_ring<NC, 2>(S, c, ring, src);
+        for (int i = ia; i <= ib; i += 3) {
+            adv_load_ring<NC, 0>(S, c, ring, src);
+            if (active) adv_row<true, NC, 0>(S, c, nullptr, P, us, vs, (size_t)i * P + col, g.gi0 + i, jl, g.nx, g.ny);
+            if (i + 1 > ib) break;
+            adv_load_ring<NC, 1>(S, c, ring, src);
+            if (active) adv_row<true, NC, 1>(S, c, nullptr, P, us, vs, (size_t)(i + 1) * P + col, g.gi0 + i + 1, jl, g.nx, g.ny);
+            if (i + 2 > ib) break;
+            adv_load_ring<NC, 2>(S, c, ring, src);
+            if (active) adv_row<true, NC, 2>(S, c, nullptr, P, us, vs, (size_t)(i + 2) * P + col, g.gi0 + i + 2, jl, g.nx, g.ny);
+        }
+    }
+    ring.drain();
+    wq_leave(wq, lane, gridDim.x * kMomWarps);
 }
 
 // ======================================================================================

@@ -112,6 +112,92 @@ struct RowRing {
     __device__ __forceinline__ void drain() { cp_async_wait<0>(); }
 };
 
+__device__ __forceinline__ void cp_async_4(unsigned smem_addr, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ float lds_f1(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+
+// RowRing plus the two columns next to a warp's strip: lane 0 also copies column jl-1 of the fields in LMASK, lane 31
+// column jl+NC of the fields in RMASK (one 4-byte cp.async each), so stencils along j need no synchronous edge loads.
+// Slot layout: NF * THREADS lanes of NC floats, then NF * WARPS pairs (left, right).
+template <int NF, int NC, int SLOTS, int THREADS, unsigned LMASK, unsigned RMASK>
+struct RowRingH {
+    static constexpr int kLane = NC * 4;
+    static constexpr int kField = THREADS * kLane;
+    static constexpr int kHalo = NF * (THREADS / 32) * 8;        // bytes of halo pairs per slot
+    static constexpr int kSlot = NF * kField + kHalo;
+    static constexpr int kBytes = SLOTS * kSlot;
+    static constexpr int kAhead = SLOTS - 2;
+    static_assert(kSlot % 16 == 0, "slots must stay 16-byte aligned");
+    unsigned base, hbase;  // shared address of this thread's lane (slot 0, field 0) / of this warp's halo pairs (slot 0)
+    unsigned wr, rd;       // slot indices
+    int row, row_end, last, pitch4;
+    bool active;
+    int lane;
+
+    __device__ __forceinline__ void init(void* smem, int tid) {
+        const unsigned s0 = (unsigned)__cvta_generic_to_shared(smem);
+        base = s0 + tid * kLane;
+        hbase = s0 + NF * kField + (tid >> 5) * 8;
+        lane = tid & 31;
+        wr = 0; rd = 0; active = false;
+    }
+    __device__ __forceinline__ void start(bool active_, int first, int end, int last_row, int pitch_floats, const float* const (&src)[NF]) {
+        active = active_; rd = wr; row = first; row_end = end; last = last_row; pitch4 = pitch_floats * 4;
+#pragma unroll
+        for (int d = 0; d < kAhead; ++d) issue(src);
+    }
+    __device__ __forceinline__ void issue(const float* const (&src)[NF]) {
+        if (active && row <= row_end) {
+            const int rr = min(max(row, 0), last);
+            const unsigned so = wr * kSlot;
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const char* gp = reinterpret_cast<const char*>(src[f]) + (long long)rr * pitch4;
+                if constexpr (NC == 4) cp_async_16(base + so + f * kField, gp);
+                else cp_async_8(base + so + f * kField, gp);
+                if (((LMASK >> f) & 1u) && lane == 0) cp_async_4(hbase + so + f * (THREADS / 32) * 8, gp - 4);
+                if (((RMASK >> f) & 1u) && lane == 31) cp_async_4(hbase + so + f * (THREADS / 32) * 8 + 4, gp + kLane);
+            }
+        }
+        cp_async_commit();
+        ++row;
+        wr = (wr + 1) % SLOTS;
+    }
+    // x[f][1..NC] = own columns, x[f][0] = column jl-1, x[f][NC+1] = column jl+NC (fields outside the masks: unspecified)
+    __device__ __forceinline__ void next(float (&x)[NF][NC + 2], const float* const (&src)[NF]) {
+        cp_async_wait<kAhead - 1>();
+        const unsigned so = rd * kSlot;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            float v[NC];
+#pragma unroll
+            for (int q = 0; q < NC; ++q) v[q] = 0.0f;
+            if (active) {
+                if constexpr (NC == 4) { const float4 t = lds_f4(base + so + f * kField); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+                else { const float2 t = lds_f2(base + so + f * kField); v[0] = t.x; v[1] = t.y; }
+            }
+#pragma unroll
+            for (int q = 0; q < NC; ++q) x[f][q + 1] = v[q];
+            if ((LMASK >> f) & 1u) {
+                x[f][0] = __shfl_up_sync(0xffffffffu, v[NC - 1], 1);
+                if (lane == 0 && active) x[f][0] = lds_f1(hbase + so + f * (THREADS / 32) * 8);
+            }
+            if ((RMASK >> f) & 1u) {
+                x[f][NC + 1] = __shfl_down_sync(0xffffffffu, v[0], 1);
+                if (lane == 31 && active) x[f][NC + 1] = lds_f1(hbase + so + f * (THREADS / 32) * 8 + 4);
+            }
+        }
+        rd = (rd + 1) % SLOTS;
+        issue(src);
+    }
+    __device__ __forceinline__ void drain() { cp_async_wait<0>(); }
+};
+
 // every bit pattern with an all-ones exponent is inf or NaN
 template <int N> __device__ __forceinline__ bool all_finite_n(const float (&x)[N]) {
     unsigned a = 0;
