@@ -215,6 +215,7 @@ int vof3d_run(Vof3Ctx* c, int istep0, int nsteps, unsigned flags);
 int vof3d_field_ptr(Vof3Ctx* c, int field, float** dev, int64_t* pitch_k, int64_t* pitch_j, int64_t* planes);
 int vof3d_field_get(Vof3Ctx* c, int field, float* host_dst);   /* F.to_numpy(), 3dvof.py:627         */
 int vof3d_field_set(Vof3Ctx* c, int field, const float* host_src);
+int vof3d_set_option(Vof3Ctx* c, int option, int value);      /* VOF_OPT_ADAPTIVE: 1 (default) second-generation kernels, 0 first */
 int vof3d_diagnostics(Vof3Ctx* c, double* mass, float* max_cfl, int64_t* courant_count);
 int64_t vof3d_launch_count(const Vof3Ctx* c);
 int vof3d_halo_ptr(Vof3Ctx* c, int field, int side, int send, float** dev, int64_t* count);

@@ -134,6 +134,7 @@ SIGNATURES = {
     "vof3d_field_set": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
     "vof3d_diagnostics": (C.c_int, [_ctx, _P(C.c_double), _P(C.c_float), _P(C.c_int64)]),
     "vof3d_launch_count": (C.c_int64, [_ctx]),
+    "vof3d_set_option": (C.c_int, [_ctx, C.c_int, C.c_int]),
     "vof3d_halo_ptr": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _P(C.c_void_p), _P(C.c_int64)]),
     "vof3d_halo_push": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p]),
 }

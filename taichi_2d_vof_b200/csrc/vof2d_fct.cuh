@@ -84,12 +84,12 @@ __device__ __forceinline__ void fct_ratios2(float td_m, float td_c, float td_p, 
         if (pp > 0.0f) {
             const float fmax = fmaxf(fmaxf(td_c, td_m), td_p);
             const float qp = (fmax - td_c) * c.dx;
-            rp = qp >= pp ? 1.0f : qp / pp;            // min(1, q/p) = 1 whenever q >= p > 0
+            rp = qp >= pp ? 1.0f : div_nz(qp, pp);     // min(1, q/p) = 1 whenever q >= p > 0; 0 / p without the slow path
         }
         if (pm > 0.0f) {
             const float fmin = fminf(fminf(td_c, td_m), td_p);
             const float qm = (td_c - fmin) * c.dx;
-            rm = qm >= pm ? 1.0f : qm / pm;
+            rm = qm >= pm ? 1.0f : div_nz(qm, pm);
         }
     }
 }

@@ -29,6 +29,7 @@ struct Vof3Ctx {
     bool has_lo, has_hi;
     int all_a, all_b, in_a, in_b;
     long long launches;
+    int opt_gen2;              // 1 (default): second-generation kernels, 0: first generation (same bits)
     float* F() { return buf[F_cur ? B3_F1 : B3_F0]; }
     float* F_alt() { return buf[F_cur ? B3_F0 : B3_F1]; }
     float* p() { return buf[p_cur ? B3_P1 : B3_P0]; }
@@ -90,6 +91,7 @@ extern "C" int vof3d_create(const VofParams* in, Vof3Ctx** out) {
     Vof3Ctx* c = new (std::nothrow) Vof3Ctx();
     if (!c) return fail(VOF_ENOMEM, "out of host memory");
     memset(c, 0, sizeof(*c));
+    c->opt_gen2 = 1;
     c->device = dev; c->g = g;
     c->lo = P.slab_lo; c->hi = P.slab_hi; c->H = P.halo;
     c->has_lo = c->lo == 1; c->has_hi = c->hi == P.nx;
@@ -237,8 +239,13 @@ static int run3_jacobi(Vof3Ctx* c, int mode) {
     dim3 grid = grid_jk(c, c->g.nz + 2, c->g.ny + 2, planes, kRows3);
 #define J3 c->g, c->k, c->p(), c->p_alt(), c->buf[B3_RHS], c->buf[B3_RHO], c->buf[B3_US], c->buf[B3_VS], c->buf[B3_WS], c->all_a, c->all_b, kRows3
     if (mode == 0) {
-        dim3 g4(cdiv(c->g.nz + 1, 128), cdiv(c->g.ny + 2, 4), cdiv(planes, kRows3));
-        k3_jacobi4<<<g4, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, kRows3);
+        if (c->opt_gen2) {
+            dim3 g5(cdiv(c->g.nz, 128), cdiv(c->g.ny + 2, 4), cdiv(planes, kRows3));
+            k3_jacobi5<<<g5, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, kRows3);
+        } else {
+            dim3 g4(cdiv(c->g.nz + 1, 128), cdiv(c->g.ny + 2, 4), cdiv(planes, kRows3));
+            k3_jacobi4<<<g4, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, kRows3);
+        }
     } else k3_jacobi<1><<<grid, kB3, 0, c->stream>>>(J3);
 #undef J3
     c->p_cur ^= 1;
@@ -437,5 +444,13 @@ extern "C" int vof3d_halo_push(Vof3Ctx* c, int field, int side, float* peer_halo
     if (!peer_halo_dst) return fail(VOF_EINVAL, "null peer destination");
     CU(cudaSetDevice(c->device));
     CU(cudaMemcpyAsync(peer_halo_dst, src, (size_t)n * sizeof(float), cudaMemcpyDefault, c->stream));
+    return VOF_OK;
+}
+
+extern "C" int vof3d_set_option(Vof3Ctx* c, int option, int value) {
+    if (!c) return fail(VOF_EINVAL, "null context");
+    if (option != VOF_OPT_ADAPTIVE) return fail(VOF_EINVAL, "3-D contexts know option VOF_OPT_ADAPTIVE only (got %d)", option);
+    if (value != 0 && value != 1) return fail(VOF_EINVAL, "adaptive must be 0 or 1");
+    c->opt_gen2 = value;
     return VOF_OK;
 }

@@ -61,6 +61,14 @@ __device__ __forceinline__ float nu_of(float F, const Consts& c) {
     return c.nu_l * f + c.nu_g * (1.0f - f);
 }
 
+// IEEE quotient with the zero numerator taken out: nvcc's division sends t = 0 (ubiquitous while the pressure front has
+// not reached a cell) through its out-of-line slow path (~35 instructions); 0 / b is a zero with the product's sign.
+__device__ __forceinline__ float div_nz(float t, float b) {
+    float r = t * (b < 0.0f ? -1.0f : 1.0f);
+    if (t != 0.0f) { asm volatile("" ::: "memory"); r = t / b; }
+    return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

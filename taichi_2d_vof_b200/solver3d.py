@@ -122,6 +122,10 @@ class VofSolver3D:
     def mass(self):
         return self.diagnostics()["mass"]
 
+    def set_option(self, option: int, value: int):
+        """VOF_OPT_ADAPTIVE: 1 (default) second-generation kernels, 0 first generation; identical results."""
+        check(self._L.vof3d_set_option(self._h, int(option), int(value)))
+
     def launch_count(self):
         return int(self._L.vof3d_launch_count(self._h))
 

@@ -22,7 +22,7 @@ def _same(s, o, fields, tag):
         assert bad.size == 0, f"{tag} field {k}: {len(bad)} cells differ, first {bad[0]}: {a[tuple(bad[0])]} vs {b[tuple(bad[0])]}"
 
 
-@pytest.mark.parametrize("shape", [(24, 24, 24), (17, 30, 150), (40, 9, 21)])
+@pytest.mark.parametrize("shape", [(24, 24, 24), (17, 30, 150), (40, 9, 21), (8, 12, 128), (6, 5, 256)])
 def test_each_kernel_in_sequence_3d(built_lib, shape):
     nx, ny, nz = shape
     P = Vof3DParams(nx=nx, ny=ny, nz=nz, Lx=0.1 * nx / 200, Ly=0.1 * ny / 200, Lz=0.1 * nz / 200)
@@ -106,3 +106,18 @@ def test_plane_slabs_equal_full_domain_3d(built_lib, nslabs):
                 a, b = grp.gather(k), getattr(full, k).to_numpy()
                 bad = np.argwhere(a != b)
                 assert bad.size == 0, f"step {step} field {k}: {len(bad)} cells differ, first {bad[0]}"
+
+
+def test_generations_identical_3d(built_lib):
+    """Second-generation 3-D kernels (default) against the first generation: 12 steps at 128 x 96 x 160, every field."""
+    from taichi_2d_vof_b200 import VofSolver3D, _lib, reference_params3d
+    out = []
+    for gen2 in (1, 0):
+        s = VofSolver3D(reference_params3d(nx=128, ny=96, nz=160, Lx=0.064, Ly=0.048, Lz=0.08))
+        s.set_option(_lib.VOF_OPT_ADAPTIVE, gen2)
+        s.set_init_F(1)
+        for _ in range(12):
+            s.step()
+        out.append({k: getattr(s, k).to_numpy() for k in CORE})
+    for k in CORE:
+        assert out[0][k].tobytes() == out[1][k].tobytes(), f"field {k} differs between the kernel generations"
