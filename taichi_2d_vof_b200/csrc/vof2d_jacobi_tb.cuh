@@ -114,7 +114,7 @@ static __device__ __noinline__ float4 jac_general_row(float4 up, float4 md, floa
         t = t - aw * d4[k];
         t = t - an * pn;
         t = t - as * ps;
-        const float q = __fdiv_rn(t, ap);
+        const float q = div_nz(t, ap);
         out[k] = (rowin && j >= 1 && j <= ny) ? q : m4[k];
     }
     return make_float4(out[0], out[1], out[2], out[3]);

@@ -112,7 +112,7 @@ k_kappa4(Grid g, Consts c, const float* __restrict__ F, float* __restrict__ kapp
                 mx = mxs; my = mys;
                 if (!(fabsf(mxs) < 1e-10f && fabsf(mys) < 1e-10f)) {   // 2dvof.py:300-306
                     const float mag = sqrtf(mxs * mxs + mys * mys);
-                    mx = mxs / mag; my = mys / mag;
+                    mx = div_nz(mxs, mag); my = div_nz(mys, mag);   // a flat interface has one zero component
                 }
             }
             mx_n[q] = mx; my_n[q + 1] = my;
@@ -286,7 +286,7 @@ k_kappa5(Grid g, Consts c, WorkQueue wq, const float* __restrict__ F, float* __r
                 mx = mxs; my = mys;
                 if (!(fabsf(mxs) < 1e-10f && fabsf(mys) < 1e-10f)) {   // 2dvof.py:300-306
                     const float mag = sqrtf(mxs * mxs + mys * mys);
-                    mx = mxs / mag; my = mys / mag;
+                    mx = div_nz(mxs, mag); my = div_nz(mys, mag);   // a flat interface has one zero component
                 }
             }
             mx_n[q] = mx; my_n[q + 1] = my;

@@ -158,7 +158,7 @@ k_jacobi(Grid g, Consts c, const float* __restrict__ p, float* __restrict__ pn,
             t = t - aw * p_m;
             t = t - an * p[o + 1];
             t = t - as * p[o - 1];
-            out = t / ap;
+            out = div_nz(t, ap);                // p = 0 ahead of the pressure front: skip nvcc's slow path for 0 / ap
         }
         pn[o] = out;
         p_m = p_c; p_c = p_p; us_c = us_p;

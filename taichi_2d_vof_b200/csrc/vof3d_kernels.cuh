@@ -445,7 +445,8 @@ __device__ __forceinline__ float f3_hi(float vel, float Fm, float Fc, float dt) 
 __device__ __forceinline__ float f3_ftd(float Fc, float lo, float hi, float dv, const Fct3C& c) {
     float s = (lo - hi) * c.m1;
     if (c.has_m2) s = s * c.m2;
-    float t = ((((Fc + s / c.d1) * c.dx) * c.dy) * c.dz) / dv;
+    // div_nz: the IEEE quotient, with zero numerators (the whole gas phase) kept off nvcc's out-of-line division path
+    float t = div_nz((((Fc + div_nz(s, c.d1)) * c.dx) * c.dy) * c.dz, dv);
     if (t > 1.0f || t < 0.0f) t = var01(t);
     return t;
 }
@@ -453,8 +454,8 @@ __device__ __forceinline__ void f3_ratios(float tm, float tc, float tp, float a_
     const float fmax = fmaxf(fmaxf(tc, tm), tp), fmin = fminf(fminf(tc, tm), tp);
     const float pp = fmaxf(0.0f, a_c) - fminf(0.0f, a_p), pm = fmaxf(0.0f, a_p) - fminf(0.0f, a_c);
     const float qp = (fmax - tc) * c.qs, qm = (tc - fmin) * c.qs;
-    rp = pp > 0.0f ? fminf(1.0f, qp / pp) : 0.0f;
-    rm = pm > 0.0f ? fminf(1.0f, qm / pm) : 0.0f;
+    rp = pp > 0.0f ? fminf(1.0f, div_nz(qp, pp)) : 0.0f;
+    rm = pm > 0.0f ? fminf(1.0f, div_nz(qm, pm)) : 0.0f;
 }
 __device__ __forceinline__ float f3_cface(float a_f, float rp_m, float rm_m, float rp_c, float rm_c) {
     return a_f >= 0.0f ? fminf(rp_c, rm_m) : fminf(rp_m, rm_c);
@@ -462,7 +463,7 @@ __device__ __forceinline__ float f3_cface(float a_f, float rp_m, float rm_m, flo
 template <bool POST>
 __device__ __forceinline__ float f3_update(float td, float a_c, float c_c, float a_p, float c_p, float dv, const Fct3C& c) {
     const float t = a_p * c_p - a_c * c_c;
-    const float fn = td - ((((t / c.d2) * c.dx) * c.dy) * c.dz) / dv;
+    const float fn = td - div_nz((((div_nz(t, c.d2)) * c.dx) * c.dy) * c.dz, dv);
     float f = var01(fn);
     if (POST) f = var01(f);
     return f;
