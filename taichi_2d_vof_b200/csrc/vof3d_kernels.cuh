@@ -442,28 +442,47 @@ struct Fct3C {
 
 __device__ __forceinline__ float f3_lo(float vel, float Fm, float Fc, float dt) { const float vd = vel * dt; return vel >= 0.0f ? vd * Fm : vd * Fc; }
 __device__ __forceinline__ float f3_hi(float vel, float Fm, float Fc, float dt) { const float vd = vel * dt; return vel <= 0.0f ? vd * Fm : vd * Fc; }
+// Exact short-cuts as in the 2-D sweeps (vof2d_fct.cuh): x + (+-0 / d) = x for the F >= +0 this code produces,
+// 0 * dx * dy * dz / dv = 0 (div_nz keeps the sign), and where both faces of a cell carry no antidiffusive flux the
+// limiter ratios are 0 and the corrective term is +-0.
 __device__ __forceinline__ float f3_ftd(float Fc, float lo, float hi, float dv, const Fct3C& c) {
-    float s = (lo - hi) * c.m1;
-    if (c.has_m2) s = s * c.m2;
-    // div_nz: the IEEE quotient, with zero numerators (the whole gas phase) kept off nvcc's out-of-line division path
-    float t = div_nz((((Fc + div_nz(s, c.d1)) * c.dx) * c.dy) * c.dz, dv);
+    const float d = lo - hi;
+    float T = Fc;
+    if (d != 0.0f) {
+        float s = d * c.m1;
+        if (c.has_m2) s = s * c.m2;
+        T = Fc + div_nz(s, c.d1);
+    }
+    float t = div_nz(((T * c.dx) * c.dy) * c.dz, dv);
     if (t > 1.0f || t < 0.0f) t = var01(t);
     return t;
 }
 __device__ __forceinline__ void f3_ratios(float tm, float tc, float tp, float a_c, float a_p, const Fct3C& c, float& rp, float& rm) {
-    const float fmax = fmaxf(fmaxf(tc, tm), tp), fmin = fminf(fminf(tc, tm), tp);
-    const float pp = fmaxf(0.0f, a_c) - fminf(0.0f, a_p), pm = fmaxf(0.0f, a_p) - fminf(0.0f, a_c);
-    const float qp = (fmax - tc) * c.qs, qm = (tc - fmin) * c.qs;
-    rp = pp > 0.0f ? fminf(1.0f, div_nz(qp, pp)) : 0.0f;
-    rm = pm > 0.0f ? fminf(1.0f, div_nz(qm, pm)) : 0.0f;
+    rp = 0.0f; rm = 0.0f;
+    if (a_c != 0.0f || a_p != 0.0f) {                 // otherwise pp = pm = 0 (or NaN never: a is finite or NaN != 0)
+        const float pp = fmaxf(0.0f, a_c) - fminf(0.0f, a_p), pm = fmaxf(0.0f, a_p) - fminf(0.0f, a_c);
+        if (pp > 0.0f) {
+            const float fmax = fmaxf(fmaxf(tc, tm), tp);
+            const float qp = (fmax - tc) * c.qs;
+            rp = fminf(1.0f, div_nz(qp, pp));
+        }
+        if (pm > 0.0f) {
+            const float fmin = fminf(fminf(tc, tm), tp);
+            const float qm = (tc - fmin) * c.qs;
+            rm = fminf(1.0f, div_nz(qm, pm));
+        }
+    }
 }
 __device__ __forceinline__ float f3_cface(float a_f, float rp_m, float rm_m, float rp_c, float rm_c) {
     return a_f >= 0.0f ? fminf(rp_c, rm_m) : fminf(rp_m, rm_c);
 }
 template <bool POST>
 __device__ __forceinline__ float f3_update(float td, float a_c, float c_c, float a_p, float c_p, float dv, const Fct3C& c) {
-    const float t = a_p * c_p - a_c * c_c;
-    const float fn = td - div_nz((((div_nz(t, c.d2)) * c.dx) * c.dy) * c.dz, dv);
+    float fn = td;
+    if (a_c != 0.0f || a_p != 0.0f) {
+        const float t = a_p * c_p - a_c * c_c;
+        fn = td - div_nz((((div_nz(t, c.d2)) * c.dx) * c.dy) * c.dz, dv);
+    }
     float f = var01(fn);
     if (POST) f = var01(f);
     return f;
