@@ -145,6 +145,17 @@ int vof2d_field_fill(VofCtx* c, int field, float value);
  * mass = sum F over owned interior cells (fp64), max_cfl = max(|u|dt/dx, |v|dt/dy),
  * residual = L-inf of (rhs - A p) over owned interior cells, courant_count = number of faces
  * with u*dt > 0.25*dx (the reference's print condition).  Any pointer may be NULL.  Synchronous. */
+/* Display kernels of the GUI loop (2dvof.py:458-492, called every 100 steps at 530-561): monitoring output only.
+   rgb_buf is (2 nx, 2 ny) fp32, C order: rgb_buf[I] = field[I // 2], velocities divided by L / 0.2.  Full-domain
+   contexts only (VOF_ESTATE on a slab). */
+enum { VOF_VIEW_VOF = 0,    /* get_vof_field   2dvof.py:458-462 */
+       VOF_VIEW_U = 1,      /* get_u_field     2dvof.py:465-470 */
+       VOF_VIEW_V = 2,      /* get_v_field     2dvof.py:473-478 */
+       VOF_VIEW_VNORM = 3   /* get_vnorm_field 2dvof.py:481-486 */ };
+int vof2d_display_field(VofCtx* c, int view, float* rgb_host);      /* kernel + rgb_buf.to_numpy() (2dvof.py:535); synchronous */
+int vof2d_display_field_dev(VofCtx* c, int view, float* rgb_dev);   /* the same into a device buffer, asynchronous */
+int vof2d_interp_velocity(VofCtx* c, float* V_host);                /* interp_velocity 2dvof.py:489-492: (nx+2, ny+2, 2) fp32 */
+
 int vof2d_diagnostics(VofCtx* c, double* mass, float* max_cfl, float* residual, int64_t* courant_count);
 
 /* ---- measurement support (new): every kernel launch is counted; with profiling on, each launch

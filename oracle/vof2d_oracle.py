@@ -424,6 +424,33 @@ class Vof2DOracle:
         self.F[...] = self._var(self.F, R(0), R(1))
 
     # --------------------------------------------------------------- main loop
+    # 2dvof.py:458-486: rgb_buf[I] = field[I // r], r = resolution[0] // nx = 2; velocities over L / 0.2
+    def _upsample(self, a):
+        P = self.P
+        return np.repeat(np.repeat(a[:P.nx, :P.ny], 2, axis=0), 2, axis=1).astype(self.real)
+
+    def get_vof_field(self):
+        return self._upsample(self.F)
+
+    def get_u_field(self):
+        return self._upsample(self.u / self.real(self.P.Lx / 0.2))
+
+    def get_v_field(self):
+        return self._upsample(self.v / self.real(self.P.Ly / 0.2))
+
+    def get_vnorm_field(self):
+        R = self.real
+        return self._upsample(np.sqrt(self.u * self.u + self.v * self.v).astype(R) / R(self.P.Ly / 0.2))
+
+    # 2dvof.py:489-492.  The reference's i-range reaches nx+1 and reads u[nx+2, j] (out of bounds, undefined): that
+    # row is left at zero here and in the CUDA kernel.
+    def interp_velocity(self):
+        P, R = self.P, self.real
+        V = np.zeros((P.nx + 2, P.ny + 2, 2), dtype=R)
+        V[1:P.nx + 1, 1:P.ny + 1, 0] = (self.u[1:P.nx + 1, 1:P.ny + 1] + self.u[2:P.nx + 2, 1:P.ny + 1]) / R(2)
+        V[1:P.nx + 1, 1:P.ny + 1, 1] = (self.v[1:P.nx + 1, 1:P.ny + 1] + self.v[1:P.nx + 1, 2:P.ny + 2]) / R(2)
+        return V
+
     def step(self):
         """One iteration of the loop body, 2dvof.py:506-528."""
         self.istep += 1

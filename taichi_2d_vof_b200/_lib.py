@@ -23,6 +23,7 @@ VOF_OPT_FCT_X_COLS = 1
 VOF_OPT_ADVECT_COLS = 2
 VOF_OPT_ADAPTIVE = 3
 VOF_OPT_CHUNK_CAP = 4
+VOF_VIEW_VOF, VOF_VIEW_U, VOF_VIEW_V, VOF_VIEW_VNORM = 0, 1, 2, 3
 VOF_STEP_MATERIALIZE_PROPS = 1
 VOF_STEP_NO_FUSION = 2
 VOF_SLAB_MIN_HALO = 13
@@ -85,6 +86,9 @@ SIGNATURES = {
     "vof2d_fct_y_sweep": (C.c_int, [_ctx]),
     "vof2d_solve_VOF_rudman": (C.c_int, [_ctx, C.c_int]),
     "vof2d_post_process_f": (C.c_int, [_ctx]),
+    "vof2d_display_field": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
+    "vof2d_display_field_dev": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
+    "vof2d_interp_velocity": (C.c_int, [_ctx, C.c_void_p]),
     "vof2d_step": (C.c_int, [_ctx, C.c_int, C.c_uint]),
     "vof2d_run": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_uint]),
     "vof2d_step_host": (C.c_int, [_ctx, C.c_int, C.c_uint] + [C.c_void_p] * 8),

@@ -643,6 +643,65 @@ extern "C" int vof2d_solve_VOF_rudman(VofCtx* c, int istep) {
 extern "C" int vof2d_post_process_f(VofCtx* c) { CHECK_CTX(c); return run_post(c); }
 
 // ------------------------------------------------------------------------------------
+// display kernels, 2dvof.py:458-492 (+ rgb_buf.to_numpy(), 535): monitoring output, full-domain contexts only
+// ------------------------------------------------------------------------------------
+static int display_dev(VofCtx* c, int view, float* rgb) {
+    if (c->g.gi0 != 0 || c->g.nrows != c->g.nx + 2) return fail(VOF_ESTATE, "display kernels need a full-domain context");
+    ++c->launches;
+    dim3 grid(cdiv(2 * c->g.ny, 256), 2 * c->g.nx);
+    const float mx = (float)(c->P.Lx / 0.2), my = (float)(c->P.Ly / 0.2);      // Python scalars, folded in double
+    switch (view) {
+        case VOF_VIEW_VOF: k_display<0><<<grid, 256, 0, c->stream>>>(c->g, c->F(), c->buf[BUF_U], c->buf[BUF_V], 1.0f, rgb); break;
+        case VOF_VIEW_U: k_display<1><<<grid, 256, 0, c->stream>>>(c->g, c->F(), c->buf[BUF_U], c->buf[BUF_V], mx, rgb); break;
+        case VOF_VIEW_V: k_display<2><<<grid, 256, 0, c->stream>>>(c->g, c->F(), c->buf[BUF_U], c->buf[BUF_V], my, rgb); break;
+        case VOF_VIEW_VNORM: k_display<3><<<grid, 256, 0, c->stream>>>(c->g, c->F(), c->buf[BUF_U], c->buf[BUF_V], my, rgb); break;
+        default: return fail(VOF_EINVAL, "unknown view %d", view);
+    }
+    return launch_ok("k_display");
+}
+extern "C" int vof2d_display_field_dev(VofCtx* c, int view, float* rgb_dev) {
+    CHECK_CTX(c);
+    if (!rgb_dev) return fail(VOF_EINVAL, "null output");
+    CU(cudaSetDevice(c->device));
+    return display_dev(c, view, rgb_dev);
+}
+extern "C" int vof2d_display_field(VofCtx* c, int view, float* rgb_host) {
+    CHECK_CTX(c);
+    if (!rgb_host) return fail(VOF_EINVAL, "null output");
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)4 * c->g.nx * c->g.ny * sizeof(float);
+    float* d = nullptr;
+    if (cudaMalloc((void**)&d, bytes) != cudaSuccess) return fail(VOF_ENOMEM, "cudaMalloc(%zu bytes) for rgb_buf failed", bytes);
+    int rc = display_dev(c, view, d);
+    if (rc == VOF_OK) {
+        cudaError_t e = cudaMemcpyAsync(rgb_host, d, bytes, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail((int)e, "rgb_buf copy failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+extern "C" int vof2d_interp_velocity(VofCtx* c, float* V_host) {
+    CHECK_CTX(c);
+    if (!V_host) return fail(VOF_EINVAL, "null output");
+    if (c->g.gi0 != 0 || c->g.nrows != c->g.nx + 2) return fail(VOF_ESTATE, "display kernels need a full-domain context");
+    CU(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)2 * (c->g.nx + 2) * (c->g.ny + 2) * sizeof(float);
+    float2* d = nullptr;
+    if (cudaMalloc((void**)&d, bytes) != cudaSuccess) return fail(VOF_ENOMEM, "cudaMalloc(%zu bytes) for V failed", bytes);
+    ++c->launches;
+    k_interp_velocity<<<dim3(cdiv(c->g.ny + 2, 256), c->g.nx + 2), 256, 0, c->stream>>>(c->g, c->buf[BUF_U], c->buf[BUF_V], d);
+    int rc = launch_ok("k_interp_velocity");
+    if (rc == VOF_OK) {
+        cudaError_t e = cudaMemcpyAsync(V_host, d, bytes, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail((int)e, "V copy failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------
 // the loop body 2dvof.py:513-528
 // ------------------------------------------------------------------------------------
 static int step_impl(VofCtx* c, int istep, unsigned flags) {

@@ -182,6 +182,39 @@ k_post_process_f(Grid g, float* __restrict__ F, int r0, int r1, int rows_per_blo
 }
 
 // ======================================================================================
+// display kernels (2dvof.py:458-492): x2 nearest-neighbour upsample of F / u / v / |V| into rgb_buf (2nx, 2ny),
+// velocities scaled by L / 0.2; cell-centred velocity V.  Monitoring only -- never on the step's path.
+// ======================================================================================
+template <int VIEW>      // 0 F, 1 u / (Lx/0.2), 2 v / (Ly/0.2), 3 sqrt(u^2 + v^2) / (Ly/0.2)
+__global__ void __launch_bounds__(256)
+k_display(Grid g, const float* __restrict__ F, const float* __restrict__ u, const float* __restrict__ v, float vmax,
+          float* __restrict__ rgb) {
+    const int J = blockIdx.x * 256 + threadIdx.x, I = blockIdx.y;
+    if (J >= 2 * g.ny) return;
+    const size_t o = (size_t)(I >> 1) * g.pitch + (J >> 1);                 // rgb_buf[I] = field[I // r], r = 2
+    float x;
+    if (VIEW == 0) x = F[o];
+    else if (VIEW == 1) x = u[o] / vmax;
+    else if (VIEW == 2) x = v[o] / vmax;
+    else x = sqrtf(u[o] * u[o] + v[o] * v[o]) / vmax;
+    rgb[(size_t)I * (2 * g.ny) + J] = x;
+}
+// V[i, j] = ((u[i,j] + u[i+1,j]) / 2, (v[i,j] + v[i,j+1]) / 2) for i in [1, nx+1], j in [1, ny] (2dvof.py:489-492).  The
+// reference's range reads u[nx+2, j], one row past the field (undefined there); that row of V is left at zero here.
+__global__ void __launch_bounds__(256)
+k_interp_velocity(Grid g, const float* __restrict__ u, const float* __restrict__ v, float2* __restrict__ V) {
+    const int j = blockIdx.x * 256 + threadIdx.x, i = blockIdx.y;
+    if (j > g.ny + 1) return;
+    float2 r = make_float2(0.0f, 0.0f);
+    if (i >= 1 && i <= g.nx && j >= 1 && j <= g.ny) {
+        const size_t o = (size_t)i * g.pitch + j;
+        r.x = (u[o] + u[o + g.pitch]) / 2.0f;
+        r.y = (v[o] + v[o + 1]) / 2.0f;
+    }
+    V[(size_t)i * (g.ny + 2) + j] = r;
+}
+
+// ======================================================================================
 // set_init_F  (2dvof.py:137-159) + find_area (102-134).  xs/ys are the fp32 node arrays.
 // ======================================================================================
 struct InitConsts {

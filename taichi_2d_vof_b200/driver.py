@@ -32,6 +32,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument('--steps', type=int, default=0, help="stop after this many steps (0 = run until interrupted, like the GUI loop)")
     p.add_argument('--nstep', type=int, default=100, help="output interval (2dvof.py:497)")
     p.add_argument('--sequence', action='store_true', help="call one C-ABI entry per reference kernel instead of the fused vof2d_step")
+    p.add_argument('--view', choices=['vof', 'u', 'v', 'vnorm', 'vectors'], default=None,
+                   help="every nstep steps also run the GUI loop's display kernel of that view (2dvof.py:530-561: the 'v' key "
+                        "cycles through these) and write output/%%06d-<view>.npy instead of painting a window")
     p.add_argument('--dump', type=str, default=None, help="write u,v,p,F (+istep) to this .npz at the end")
     p.add_argument('--device', type=int, default=0)
     return p
@@ -81,6 +84,10 @@ def main(argv=None) -> int:
                       f'VOF volume {d["mass"]:.6e}, max CFL {d["max_cfl"]:.3e}, {rate:.1f} steps/s')
                 if d["courant_count"]:
                     print(f'U/V velocity courant number > 1 on {d["courant_count"]} faces')   # 2dvof.py:274-280
+                if args.view:               # 2dvof.py:533-561, headless: rgb_buf / V to disk
+                    img = {'vof': s.get_vof_field, 'u': s.get_u_field, 'v': s.get_v_field, 'vnorm': s.get_vnorm_field,
+                           'vectors': s.interp_velocity}[args.view]()
+                    np.save(f'output/{istep // nstep - 1:06d}-{args.view}.npy', img)
                 if SAVE_FIG:                # 2dvof.py:563-571
                     count = istep // nstep - 1
                     Fnp = s.F.to_numpy()

@@ -185,6 +185,29 @@ class VofSolver2D:
     def post_process_f(self):
         check(self._L.vof2d_post_process_f(self._h))
 
+    # ---- display kernels of the GUI loop (2dvof.py:458-492): each returns what `rgb_buf.to_numpy()` / `V.to_numpy()` holds
+    def _display(self, view):
+        out = np.empty((2 * self.nx, 2 * self.ny), dtype=np.float32)
+        check(self._L.vof2d_display_field(self._h, view, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def get_vof_field(self):
+        return self._display(_lib.VOF_VIEW_VOF)
+
+    def get_u_field(self):
+        return self._display(_lib.VOF_VIEW_U)
+
+    def get_v_field(self):
+        return self._display(_lib.VOF_VIEW_V)
+
+    def get_vnorm_field(self):
+        return self._display(_lib.VOF_VIEW_VNORM)
+
+    def interp_velocity(self):
+        out = np.empty((self.nx + 2, self.ny + 2, 2), dtype=np.float32)
+        check(self._L.vof2d_interp_velocity(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     # ---- the loop body
     def step_sequence(self):
         """2dvof.py:506-528 literally: one C-ABI call per reference kernel call."""

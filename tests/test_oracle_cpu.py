@@ -172,3 +172,20 @@ def test_3d_known_answers():
     for istep in (1, 2, 3):
         o.istep = istep; o.solve_VOF_rudman()
     assert calls == [1, 2, 0, 2, 0, 1, 0, 1, 2]
+
+
+def test_display_kernels_semantics():
+    """2dvof.py:458-492: rgb_buf[I] = field[I // 2] on a (2nx, 2ny) buffer, velocities over L / 0.2; V is cell-centred."""
+    P = Vof2DParams(nx=12, ny=10, Lx=0.006, Ly=0.005)
+    o = Vof2DOracle(P); o.set_init_F(1)
+    rng = np.random.default_rng(5)
+    o.u[...] = rng.random(o.u.shape, dtype=np.float32); o.v[...] = rng.random(o.v.shape, dtype=np.float32)
+    rgb = o.get_vof_field()
+    assert rgb.shape == (24, 20) and rgb.dtype == np.float32
+    for I in ((0, 0), (1, 1), (5, 7), (23, 19)):
+        assert rgb[I] == o.F[I[0] // 2, I[1] // 2]
+    assert o.get_u_field()[7, 3] == np.float32(o.u[3, 1] / np.float32(P.Lx / 0.2))
+    assert o.get_vnorm_field()[2, 9] == np.float32(np.sqrt(o.u[1, 4] * o.u[1, 4] + o.v[1, 4] * o.v[1, 4]) / np.float32(P.Ly / 0.2))
+    V = o.interp_velocity()
+    assert V.shape == (14, 12, 2) and V[3, 4, 0] == (o.u[3, 4] + o.u[4, 4]) / np.float32(2) and V[3, 4, 1] == (o.v[3, 4] + o.v[3, 5]) / np.float32(2)
+    assert not V[0].any() and not V[:, 0].any() and not V[P.nx + 1].any()

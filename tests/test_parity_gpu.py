@@ -387,3 +387,24 @@ def test_full_size_properties_8192(built_lib):
     t.F.from_numpy(np.ascontiguousarray(F.T)); t.v.from_numpy(np.ascontiguousarray(u.T))
     s.fct_x_sweep(); t.fct_y_sweep()
     assert np.array_equal(s.F.to_numpy(), t.F.to_numpy().T)
+
+
+def test_display_kernels_match_oracle(built_lib):
+    """get_vof_field / get_u_field / get_v_field / get_vnorm_field / interp_velocity (2dvof.py:458-492)."""
+    P = Vof2DParams(nx=96, ny=130, Lx=0.048, Ly=0.065)
+    o = Vof2DOracle(P); o.set_init_F(3)
+    s = _solver(P); s.set_init_F(3)
+    for _ in range(30):
+        o.step(); s.step()
+    for name in ("get_vof_field", "get_u_field", "get_v_field", "get_vnorm_field", "interp_velocity"):
+        a, b = getattr(s, name)(), getattr(o, name)()
+        assert a.shape == b.shape and a.dtype == b.dtype
+        assert np.array_equal(a, b), f"{name}: {(a != b).sum()} elements differ"
+    assert s.get_vof_field().shape == (2 * P.nx, 2 * P.ny)
+
+
+def test_display_kernels_refuse_slabs(built_lib):
+    from taichi_2d_vof_b200 import VofSolver2D, reference_params
+    s = VofSolver2D(reference_params(nx=64, ny=64, slab=(1, 32), halo=16))
+    with pytest.raises(Exception):
+        s.get_vof_field()
