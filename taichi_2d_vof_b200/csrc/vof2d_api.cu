@@ -584,8 +584,8 @@ static int run_fct_y(VofCtx* c, bool post) {
 #define FYA c->g, c->fcty, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b, rpw, nstrips
     if (c->opt_adaptive) {
         WorkQueue wq{c->diag->wq, nwarps};
-        if (post) launch_queue(c, k_fct_y5<true>, 5, kFctYWarps, nwarps, c->g, c->fcty, wq, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b, rpw, nstrips);
-        else launch_queue(c, k_fct_y5<false>, 6, kFctYWarps, nwarps, c->g, c->fcty, wq, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b, rpw, nstrips);
+        if (post) launch_queue(c, k_fct_y5<true, FctOps2, false>, 5, kFctYWarps, nwarps, c->g, c->fcty, wq, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b, rpw, nstrips, 0);
+        else launch_queue(c, k_fct_y5<false, FctOps2, false>, 6, kFctYWarps, nwarps, c->g, c->fcty, wq, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b, rpw, nstrips, 0);
     } else {
         if (post) k_fct_y4<true, false><<<grid, 32 * kFctYWarps, 0, c->stream>>>(FYA);
         else k_fct_y4<false, false><<<grid, 32 * kFctYWarps, 0, c->stream>>>(FYA);

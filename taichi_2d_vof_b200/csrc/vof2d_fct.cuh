@@ -206,6 +206,28 @@ k_fct_x4(Grid g, FctC c, const float* __restrict__ Fin, const float* __restrict_
     }
 }
 
+// The expressions of one FCT sweep as a policy, so that the second-generation y-sweep kernel (stencil along the
+// contiguous axis) also serves the z-sweep of the 3-D solver (FctOps3 in vof3d_kernels.cuh).
+struct FctOps2 {                                   // 2dvof.py:321-448
+    using C = FctC;
+    static __device__ __forceinline__ void face(float vel, float F_m, float F_c, const C& c, float& lo, float& a) { fct_face(vel, F_m, F_c, c, lo, a); }
+    static __device__ __forceinline__ float lo_uniform(float vel, float c0, const C& c) { return (vel * c.dt) * c0; }
+    static __device__ __forceinline__ float dv(const C& c, float dvel) { return c.dxdy - c.dtd * dvel; }
+    static __device__ __forceinline__ float td_one(const C& c) { return fct_td_one(c); }
+    static __device__ __forceinline__ float ftd(float F_c, float lo_c, float lo_p, float dv, bool interior, const C& c, float td_one) {
+        return fct_ftd3(F_c, lo_c, lo_p, dv, interior, c, td_one);
+    }
+    static __device__ __forceinline__ void ratios(float td_m, float td_c, float td_p, float a_c, float a_p, bool interior, const C& c,
+                                                  float& rp, float& rm) { fct_ratios2(td_m, td_c, td_p, a_c, a_p, interior, c, rp, rm); }
+    static __device__ __forceinline__ float cface(float a_f, float rp_m, float rm_m, float rp_c, float rm_c, bool valid) {
+        return fct_cface2(a_f, rp_m, rm_m, rp_c, rm_c, valid);
+    }
+    template <bool POST>
+    static __device__ __forceinline__ float update(float td_c, float a_c, float c_c, float a_p, float c_p, float dv, const C& c) {
+        return fct_update2<POST>(td_c, a_c, c_c, a_p, c_p, dv, c);
+    }
+};
+
 // --------------------------------------------------------------------------------------
 // x-sweep, second generation: the same per-cell arithmetic (fct_face .. fct_update2), fed by the per-lane cp.async
 // ring of vof2d_stream.cuh, scheduled through a work queue, with two warp-uniform short-cuts for the bulk of a
@@ -502,15 +524,19 @@ k_fct_y4(Grid g, FctC c, const float* __restrict__ Fin, const float* __restrict_
 // vd*c - vd*c = +0 (finite vd) and limiter, face limiter and corrective update are no-ops: F' = var(Ftd).  For c = 0
 // also Ftd = 0 (0 * dx * dy / dv), so the row is 0.  The test costs five compares and one vote per lane and row.
 constexpr int kFctYSlots = 8;
-template <bool POST>
+// X = the sweep's expressions (FctOps2 / FctOps3).  PLANES = false: the rows are the rows i of a 2-D field.  PLANES = true
+// (3-D z-sweep): row r is the k-line (plane r / rows_per_plane, j = r % rows_per_plane) of a field whose planes are
+// rows_per_plane = ny3 + 2 lines apart, g.ny is the number of cells along k and a row is interior when both its plane
+// and its j are.
+template <bool POST, class X, bool PLANES>
 __global__ void __launch_bounds__(32 * kFctYWarps)
-k_fct_y5(Grid g, FctC c, WorkQueue wq, const float* __restrict__ Fin, const float* __restrict__ v, float* __restrict__ Fout,
-         int r0, int r1, int rows_per_warp, int nstrips) {
+k_fct_y5(Grid g, typename X::C c, WorkQueue wq, const float* __restrict__ Fin, const float* __restrict__ v, float* __restrict__ Fout,
+         int r0, int r1, int rows_per_warp, int nstrips, int rows_per_plane) {
     constexpr bool ADAPT = true;
     using Ring = RowRing<2, 4, kFctYSlots, 32 * kFctYWarps>;
     __shared__ __align__(16) unsigned char ring_mem[Ring::kBytes];
     const int lane = threadIdx.x & 31;
-    const float td_one = fct_td_one(c);
+    const float td_one = X::td_one(c);
     Ring ring;
     ring.init(ring_mem, threadIdx.x);
     for (;;) {
@@ -545,8 +571,14 @@ k_fct_y5(Grid g, FctC c, WorkQueue wq, const float* __restrict__ Fin, const floa
         ring.next(X, src);
         const float (&F)[4] = X[0];
         const float (&vv)[4] = X[1];
-        const int gi = g.gi0 + i;
-        const bool rowin = gi >= 1 && gi <= g.nx;
+        bool rowin;
+        if (!PLANES) {
+            const int gi = g.gi0 + i;
+            rowin = gi >= 1 && gi <= g.nx;
+        } else {
+            const int plane = i / rows_per_plane, jj = i - plane * rows_per_plane, gi = g.gi0 + plane;
+            rowin = gi >= 1 && gi <= g.nx && jj >= 1 && jj <= rows_per_plane - 2;
+        }
         const float v_p4 = __shfl_down_sync(0xffffffffu, vv[0], 1);    // v[jl+4]
         if (strip == 0 && lane == 0) Fout[(size_t)i * P] = F[3];       // ghost column 0 (jl + 3 == 0)
         if (ADAPT) {
@@ -564,12 +596,12 @@ k_fct_y5(Grid g, FctC c, WorkQueue wq, const float* __restrict__ Fin, const floa
                     } else {
                         float lo[5];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) lo[k] = (vv[k] * c.dt) * c0;
-                        lo[4] = (v_p4 * c.dt) * c0;
+                        for (int k = 0; k < 4; ++k) lo[k] = X::lo_uniform(vv[k], c0, c);
+                        lo[4] = X::lo_uniform(v_p4, c0, c);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const float dv = c.dxdy - c.dtd * ((k < 3 ? vv[k + 1] : v_p4) - vv[k]);
-                            const float td = fct_ftd3(F[k], lo[k], lo[k + 1], dv, cin[k + 1], c, td_one);
+                            const float dv = X::dv(c, (k < 3 ? vv[k + 1] : v_p4) - vv[k]);
+                            const float td = X::ftd(F[k], lo[k], lo[k + 1], dv, cin[k + 1], c, td_one);
                             float f = var01(td);
                             if (POST) f = var01(f);
                             out[k] = (rowin && cin[k + 1]) ? f : F[k];
@@ -583,31 +615,31 @@ k_fct_y5(Grid g, FctC c, WorkQueue wq, const float* __restrict__ Fin, const floa
         const float F_m1 = __shfl_up_sync(0xffffffffu, F[3], 1);       // F[jl-1]
         float lo[5], a[5];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) fct_face(vv[k], k ? F[k - 1] : F_m1, F[k], c, lo[k], a[k]);
+        for (int k = 0; k < 4; ++k) X::face(vv[k], k ? F[k - 1] : F_m1, F[k], c, lo[k], a[k]);
         lo[4] = __shfl_down_sync(0xffffffffu, lo[0], 1);
         a[4] = __shfl_down_sync(0xffffffffu, a[0], 1);
         float dv[4], td[6];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            dv[k] = c.dxdy - c.dtd * ((k < 3 ? vv[k + 1] : v_p4) - vv[k]);
-            td[k + 1] = fct_ftd3(F[k], lo[k], lo[k + 1], dv[k], cin[k + 1], c, td_one);
+            dv[k] = X::dv(c, (k < 3 ? vv[k + 1] : v_p4) - vv[k]);
+            td[k + 1] = X::ftd(F[k], lo[k], lo[k + 1], dv[k], cin[k + 1], c, td_one);
         }
         td[0] = __shfl_up_sync(0xffffffffu, td[4], 1);
         td[5] = __shfl_down_sync(0xffffffffu, td[1], 1);
         float rp[5], rm[5];   // index k+1 = cell jl+k; index 0 = cell jl-1
 #pragma unroll
-        for (int k = 0; k < 4; ++k) fct_ratios2(td[k], td[k + 1], td[k + 2], a[k], a[k + 1], cin[k + 1], c, rp[k + 1], rm[k + 1]);
+        for (int k = 0; k < 4; ++k) X::ratios(td[k], td[k + 1], td[k + 2], a[k], a[k + 1], cin[k + 1], c, rp[k + 1], rm[k + 1]);
         rp[0] = __shfl_up_sync(0xffffffffu, rp[4], 1);
         rm[0] = __shfl_up_sync(0xffffffffu, rm[4], 1);
         float cf[5];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) cf[k] = fct_cface2(a[k], rp[k], rm[k], rp[k + 1], rm[k + 1], fvalid[k]);
+        for (int k = 0; k < 4; ++k) cf[k] = X::cface(a[k], rp[k], rm[k], rp[k + 1], rm[k + 1], fvalid[k]);
         cf[4] = __shfl_down_sync(0xffffffffu, cf[0], 1);
         if (store_lane) {
             float out[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float f = fct_update2<POST>(td[k + 1], a[k], cf[k], a[k + 1], cf[k + 1], dv[k], c);
+                const float f = X::template update<POST>(td[k + 1], a[k], cf[k], a[k + 1], cf[k + 1], dv[k], c);
                 out[k] = (rowin && cin[k + 1]) ? f : F[k];             // ghost rows / columns pass through
             }
             *reinterpret_cast<float4*>(Fo + (size_t)i * P) = make_float4(out[0], out[1], out[2], out[3]);

@@ -29,6 +29,7 @@ struct Vof3Ctx {
     bool has_lo, has_hi;
     int all_a, all_b, in_a, in_b;
     long long launches;
+    int sm_count, resident_y5[2];
     int opt_gen2;              // 1 (default): second-generation kernels, 0: first generation (same bits)
     float* F() { return buf[F_cur ? B3_F1 : B3_F0]; }
     float* F_alt() { return buf[F_cur ? B3_F0 : B3_F1]; }
@@ -154,6 +155,7 @@ extern "C" int vof3d_create(const VofParams* in, Vof3Ctx** out) {
     c->own_stream = true;
     {   // prove the reciprocal division by the interior diagonal exact (every fp32 numerator against __fdiv_rn)
         unsigned long long* bad = &c->diag->courant_count;
+        c->sm_count = prop.multiProcessorCount;
         k_check_div_by_const<<<prop.multiProcessorCount * 8, 256, 0, c->stream>>>(c->jac.dv, bad);
         unsigned long long h = 1;
         CU(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
@@ -276,6 +278,25 @@ static int run3_fct(Vof3Ctx* c, int axis, bool post) {
         dim3 grid(cdiv(c->g.nz + 2, kB3), planes);
         if (post) k3_fct_strided<1, true><<<grid, kB3, 0, c->stream>>>(c->g, c->fct[1], c->F(), vel, c->F_alt(), c->all_a, c->all_b, 0);
         else k3_fct_strided<1, false><<<grid, kB3, 0, c->stream>>>(c->g, c->fct[1], c->F(), vel, c->F_alt(), c->all_a, c->all_b, 0);
+    } else if (c->opt_gen2) {
+        // z-sweep on the second-generation 2-D y-sweep kernel: rows = all (i, j) lines of the local planes
+        Grid g2{};
+        g2.nx = c->g.nx; g2.ny = c->g.nz; g2.gi0 = c->g.gi0; g2.pitch = c->g.pk;
+        const int rpp = c->g.ny + 2;
+        g2.nrows = c->g.nrows * rpp;
+        const int r0 = c->all_a * rpp, r1 = (c->all_b + 1) * rpp - 1;
+        const int nstrips = cdiv(c->g.nz + 1, kFctYValid), rpw = 16;
+        const int nitems = nstrips * cdiv(r1 - r0 + 1, rpw);
+        WorkQueue wq{c->diag->wq, nitems};
+        if (!c->resident_y5[post ? 1 : 0]) {
+            int nb = 0;
+            auto kern = post ? k_fct_y5<true, FctOps3, true> : k_fct_y5<false, FctOps3, true>;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * kFctYWarps, 0) != cudaSuccess) nb = 1;
+            c->resident_y5[post ? 1 : 0] = std::max(1, nb) * c->sm_count;
+        }
+        const int blocks = std::min(cdiv(nitems, kFctYWarps), c->resident_y5[post ? 1 : 0]);
+        if (post) k_fct_y5<true, FctOps3, true><<<blocks, 32 * kFctYWarps, 0, c->stream>>>(g2, c->fct[2], wq, c->F(), vel, c->F_alt(), r0, r1, rpw, nstrips, rpp);
+        else k_fct_y5<false, FctOps3, true><<<blocks, 32 * kFctYWarps, 0, c->stream>>>(g2, c->fct[2], wq, c->F(), vel, c->F_alt(), r0, r1, rpw, nstrips, rpp);
     } else {
         constexpr int TR = 8, TK = 128;
         const long long rows = (long long)(c->all_b - c->all_a + 1) * (c->g.ny + 2);

@@ -5,6 +5,7 @@
 // 2-D kernels (order-exact fp32, no FMA contraction).  kappa is never computed by 3dvof.py (line 607), so the
 // CSF terms are exactly +-0 and are not evaluated.
 #pragma once
+#include "vof2d_fct.cuh"
 #include "vof2d_jacobi_tb.cuh"
 #include "vof_common.cuh"
 
@@ -488,6 +489,51 @@ __device__ __forceinline__ float f3_update(float td, float a_c, float c_c, float
     return f;
 }
 
+// The 3-D expressions as the policy of the second-generation kernels of vof2d_fct.cuh (the z-sweep runs on k_fct_y5:
+// stencil along the contiguous axis by shuffles, rows = the (i, j) lines of the field).
+struct FctOps3 {                                   // 3dvof.py:366-541
+    using C = Fct3C;
+    static __device__ __forceinline__ void face(float vel, float F_m, float F_c, const C& c, float& lo, float& a) {
+        lo = f3_lo(vel, F_m, F_c, c.dt);
+        a = f3_hi(vel, F_m, F_c, c.dt) - lo;
+    }
+    static __device__ __forceinline__ float lo_uniform(float vel, float c0, const C& c) { return (vel * c.dt) * c0; }
+    static __device__ __forceinline__ float dv(const C& c, float dvel) { return c.vol - c.dtd * dvel; }
+    static __device__ __forceinline__ float td_one(const C& c) {      // a full cell whose faces move alike: a constant
+        float t = div_nz(((1.0f * c.dx) * c.dy) * c.dz, c.vol);
+        if (t > 1.0f || t < 0.0f) t = var01(t);
+        return t;
+    }
+    static __device__ __forceinline__ float ftd(float Fc, float lo, float hi, float dv, bool interior, const C& c, float td_one) {
+        const float d = lo - hi;
+        float T = Fc;
+        if (d != 0.0f) {
+            float s = d * c.m1;
+            if (c.has_m2) s = s * c.m2;
+            T = Fc + div_nz(s, c.d1);
+        }
+        float t;
+        if (T == 1.0f && dv == c.vol) t = td_one;
+        else {
+            t = div_nz(((T * c.dx) * c.dy) * c.dz, dv);
+            if (t > 1.0f || t < 0.0f) t = var01(t);
+        }
+        return interior ? t : 0.0f;
+    }
+    static __device__ __forceinline__ void ratios(float td_m, float td_c, float td_p, float a_c, float a_p, bool interior, const C& c,
+                                                  float& rp, float& rm) {
+        rp = 0.0f; rm = 0.0f;
+        if (interior) f3_ratios(td_m, td_c, td_p, a_c, a_p, c, rp, rm);
+    }
+    static __device__ __forceinline__ float cface(float a_f, float rp_m, float rm_m, float rp_c, float rm_c, bool valid) {
+        return valid ? f3_cface(a_f, rp_m, rm_m, rp_c, rm_c) : 0.0f;
+    }
+    template <bool POST>
+    static __device__ __forceinline__ float update(float td_c, float a_c, float c_c, float a_p, float c_p, float dv, const C& c) {
+        return f3_update<POST>(td_c, a_c, c_c, a_p, c_p, dv, c);
+    }
+};
+
 // Sweep along a strided axis (x: stride pj, y: stride pk): one thread per line position, the chain of radius 3
 // rolls through registers exactly as in the 2-D x-sweep.  `n` = interior cells along the axis, `goff` = global
 // index of local index 0 along the axis (gi0 for x, 0 for y), `la..lb` = local interior range to produce.
@@ -652,6 +698,7 @@ struct Diag3 {
     unsigned int max_cfl_bits;
     unsigned int pad;
     unsigned long long courant_count;
+    unsigned int wq[2];          // WorkQueue counters of the queue-scheduled kernels (vof2d_stream.cuh), zero between launches
 };
 
 __global__ void __launch_bounds__(256)
