@@ -553,13 +553,13 @@ static int run_fct_x(VofCtx* c, bool post) {
 #define FXA c->g, c->fctx, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, rpc, nstrips
     if (c->opt_adaptive) {
         WorkQueue wq{c->diag->wq, nwarps};
-#define FXQ c->g, c->fctx, wq, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, rpc, nstrips
+#define FXQ c->g, c->fctx, wq, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, rpc, nstrips, 1, 0LL, 0, 0
         if (nc == 2) {
-            if (post) launch_queue(c, k_fct_x5<true, 2>, 0, kFctXWarps, nwarps, FXQ);
-            else launch_queue(c, k_fct_x5<false, 2>, 1, kFctXWarps, nwarps, FXQ);
+            if (post) launch_queue(c, k_fct_x5<true, 2, FctOps2, false>, 0, kFctXWarps, nwarps, FXQ);
+            else launch_queue(c, k_fct_x5<false, 2, FctOps2, false>, 1, kFctXWarps, nwarps, FXQ);
         } else {
-            if (post) launch_queue(c, k_fct_x5<true, 4>, 2, kFctXWarps, nwarps, FXQ);
-            else launch_queue(c, k_fct_x5<false, 4>, 3, kFctXWarps, nwarps, FXQ);
+            if (post) launch_queue(c, k_fct_x5<true, 4, FctOps2, false>, 2, kFctXWarps, nwarps, FXQ);
+            else launch_queue(c, k_fct_x5<false, 4, FctOps2, false>, 3, kFctXWarps, nwarps, FXQ);
         }
 #undef FXQ
     } else if (nc == 2) {

@@ -241,23 +241,38 @@ struct FctOps2 {                                   // 2dvof.py:321-448
 // --------------------------------------------------------------------------------------
 constexpr int kFctXSlots = 8;                  // ring slots per lane and field (6 rows in flight)
 
-template <bool POST, int NC>
+// X = the sweep's expressions (FctOps2 / FctOps3).  BATCH = false: one 2-D field.  BATCH = true (3-D x- and y-sweeps):
+// nbatch independent 2-D problems `batch_stride` floats apart (x-sweep: the j-lines of every plane, marching i with
+// pitch = plane stride; y-sweep: the planes, marching j with pitch = line stride); problems outside the interior
+// [batch_lo, batch_hi] (ghost lines / ghost planes) are copied through.
+template <bool POST, int NC, class X, bool BATCH>
 __global__ void __launch_bounds__(32 * kFctXWarps)
-k_fct_x5(Grid g, FctC c, WorkQueue wq, const float* __restrict__ Fin, const float* __restrict__ u, float* __restrict__ Fout,
-         int r0, int r1, int rows_per_chunk, int nstrips) {
+k_fct_x5(Grid g, typename X::C c, WorkQueue wq, const float* __restrict__ Fin0, const float* __restrict__ u0, float* __restrict__ Fout0,
+         int r0, int r1, int rows_per_chunk, int nstrips, int nbatch, long long batch_stride, int batch_lo, int batch_hi) {
     using Ring = RowRing<2, NC, kFctXSlots, 32 * kFctXWarps>;
     __shared__ __align__(16) unsigned char ring_mem[Ring::kBytes];
     const int lane = threadIdx.x & 31;
     const int P = g.pitch, last = g.nrows - 1;
     const int P4i = P * 4;
     const long long P4 = P4i;
-    const float td_one = fct_td_one(c);
+    const float td_one = X::td_one(c);
     Ring ring;
     ring.init(ring_mem, threadIdx.x);
     for (;;) {
     const int item = wq_claim(wq, lane);
     if (item >= wq.nitems) break;
-    const int strip = item % nstrips, chunk = item / nstrips;
+    const int strip = item % nstrips;
+    int chunk = item / nstrips;
+    const float* Fin = Fin0;
+    const float* u = u0;
+    float* Fout = Fout0;
+    bool batch_in = true;
+    if (BATCH) {
+        const int bi = chunk % nbatch;
+        chunk /= nbatch;
+        Fin += bi * batch_stride; u += bi * batch_stride; Fout += bi * batch_stride;
+        batch_in = bi >= batch_lo && bi <= batch_hi;
+    }
     const int ia = r0 + chunk * rows_per_chunk;
     const int ib = min(r1, ia + rows_per_chunk - 1);
     const int jl = 1 + 32 * NC * strip + NC * lane;
@@ -273,6 +288,12 @@ k_fct_x5(Grid g, FctC c, WorkQueue wq, const float* __restrict__ Fin, const floa
     if (active && hi_wall) { float t[NC]; ldv(Fc, ib + 1, t); VecN<NC>::st(reinterpret_cast<float*>(Fo + (ib + 1) * P4), t); }
     if (strip == 0 && lane == 0) {
         for (int i = ia - (lo_wall ? 1 : 0); i <= ib + (hi_wall ? 1 : 0); ++i) Fout[(size_t)i * P] = Fin[(size_t)i * P];
+    }
+    if (BATCH && !batch_in) {                     // ghost line / ghost plane: the sweep leaves it alone
+        if (active) {
+            for (int i = ia; i <= ib; ++i) { float t[NC]; ldv(Fc, i, t); VecN<NC>::st(reinterpret_cast<float*>(Fo + i * P4), t); }
+        }
+        continue;
     }
     bool colin[NC];
 #pragma unroll
@@ -294,7 +315,7 @@ k_fct_x5(Grid g, FctC c, WorkQueue wq, const float* __restrict__ Fin, const floa
     auto reset_state = [&]() {          // what 7 all-zero rows leave in the pipeline (= the start of a chunk)
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
-            lo1[q] = (u1[q] * c.dt) * 0.0f;
+            lo1[q] = X::lo_uniform(u1[q], 0.0f, c);
             a1[q] = a2[q] = a3[q] = 0.f; td1[q] = td2[q] = td3[q] = 0.f;
             dv1[q] = dv2[q] = dv3[q] = 1.f; rp2[q] = rm2[q] = 0.f; c2[q] = 0.f;
         }
@@ -337,9 +358,9 @@ k_fct_x5(Grid g, FctC c, WorkQueue wq, const float* __restrict__ Fin, const floa
 #pragma unroll
             for (int q = 0; q < NC; ++q) {
                 float lo0;
-                fct_face(uk[q], F1[q], Fk[q], c, lo0, a0[q]);                                // face k
-                const float dv_n = c.dxdy - c.dtd * (uk[q] - u1[q]);                         // cell k-1
-                const float td_n = fct_ftd3(F1[q], lo1[q], lo0, dv_n, in1, c, td_one);
+                X::face(uk[q], F1[q], Fk[q], c, lo0, a0[q]);                                 // face k
+                const float dv_n = X::dv(c, uk[q] - u1[q]);                                  // cell k-1
+                const float td_n = X::ftd(F1[q], lo1[q], lo0, dv_n, in1, c, td_one);
                 td3[q] = td2[q]; td2[q] = td1[q]; td1[q] = td_n;
                 dv3[q] = dv2[q]; dv2[q] = dv1[q]; dv1[q] = dv_n;
                 lo1[q] = lo0;
@@ -358,9 +379,9 @@ k_fct_x5(Grid g, FctC c, WorkQueue wq, const float* __restrict__ Fin, const floa
 #pragma unroll
                 for (int q = 0; q < NC; ++q) {
                     float rp_n, rm_n;
-                    fct_ratios2(td3[q], td2[q], td1[q], a2[q], a1[q], in2, c, rp_n, rm_n);       // cell k-2
-                    const float c_n = fct_cface2(a2[q], rp2[q], rm2[q], rp_n, rm_n, face2);      // face k-2
-                    out[q] = fct_update2<POST>(td3[q], a3[q], c2[q], a2[q], c_n, dv3[q], c);     // cell k-3
+                    X::ratios(td3[q], td2[q], td1[q], a2[q], a1[q], in2, c, rp_n, rm_n);         // cell k-2
+                    const float c_n = X::cface(a2[q], rp2[q], rm2[q], rp_n, rm_n, face2);        // face k-2
+                    out[q] = X::template update<POST>(td3[q], a3[q], c2[q], a2[q], c_n, dv3[q], c);   // cell k-3
                     rp2[q] = rp_n; rm2[q] = rm_n; c2[q] = c_n;
                 }
             }

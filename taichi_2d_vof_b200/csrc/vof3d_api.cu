@@ -10,6 +10,8 @@ using vofhost::node_coords;
 
 enum { B3_F0 = 0, B3_F1, B3_U, B3_V, B3_W, B3_P0, B3_P1, B3_US, B3_VS, B3_WS, B3_RHS, B3_RHO, B3_NU, B3_COUNT };
 
+constexpr int kJacRows3 = 16;  // planes one block of the second-generation 7-point sweep marches (tunable: VOF_OPT_CHUNK_CAP)
+
 struct Vof3Ctx {
     VofParams P;
     Grid3 g;
@@ -29,7 +31,8 @@ struct Vof3Ctx {
     bool has_lo, has_hi;
     int all_a, all_b, in_a, in_b;
     long long launches;
-    int sm_count, resident_y5[2];
+    int sm_count, resident[8];  // resident blocks (whole device) of the queue-scheduled kernels, by variant
+    int opt_jac_rows;          // planes one block of k3_jacobi5 marches
     int opt_gen2;              // 1 (default): second-generation kernels, 0: first generation (same bits)
     float* F() { return buf[F_cur ? B3_F1 : B3_F0]; }
     float* F_alt() { return buf[F_cur ? B3_F0 : B3_F1]; }
@@ -93,6 +96,7 @@ extern "C" int vof3d_create(const VofParams* in, Vof3Ctx** out) {
     if (!c) return fail(VOF_ENOMEM, "out of host memory");
     memset(c, 0, sizeof(*c));
     c->opt_gen2 = 1;
+    c->opt_jac_rows = kJacRows3;
     c->device = dev; c->g = g;
     c->lo = P.slab_lo; c->hi = P.slab_hi; c->H = P.halo;
     c->has_lo = c->lo == 1; c->has_hi = c->hi == P.nx;
@@ -242,8 +246,9 @@ static int run3_jacobi(Vof3Ctx* c, int mode) {
 #define J3 c->g, c->k, c->p(), c->p_alt(), c->buf[B3_RHS], c->buf[B3_RHO], c->buf[B3_US], c->buf[B3_VS], c->buf[B3_WS], c->all_a, c->all_b, kRows3
     if (mode == 0) {
         if (c->opt_gen2) {
-            dim3 g5(cdiv(c->g.nz, 128), cdiv(c->g.ny + 2, 4), cdiv(planes, kRows3));
-            k3_jacobi5<<<g5, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, kRows3);
+            const int rows = std::max(1, std::min(c->opt_jac_rows, planes));
+            dim3 g5(cdiv(c->g.nz, 128), cdiv(c->g.ny + 2, 4), cdiv(planes, rows));
+            k3_jacobi5<<<g5, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, rows);
         } else {
             dim3 g4(cdiv(c->g.nz + 1, 128), cdiv(c->g.ny + 2, 4), cdiv(planes, kRows3));
             k3_jacobi4<<<g4, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, kRows3);
@@ -265,9 +270,48 @@ static int run3_project(Vof3Ctx* c, bool inl) {
 #undef P3
     return launch_ok("k3_project");
 }
+// persistent launch of a queue-scheduled kernel (resident blocks asked once per variant)
+template <typename K, typename... Args>
+static void launch_queue3(Vof3Ctx* c, K kern, int slot, int warps_per_block, int nitems, Args... args) {
+    if (!c->resident[slot]) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * warps_per_block, 0) != cudaSuccess) nb = 1;
+        c->resident[slot] = std::max(1, nb) * c->sm_count;
+    }
+    const int blocks = std::min(cdiv(nitems, warps_per_block), c->resident[slot]);
+    kern<<<blocks, 32 * warps_per_block, 0, c->stream>>>(args...);
+}
+
 static int run3_fct(Vof3Ctx* c, int axis, bool post) {
     ++c->launches;
     const float* vel = c->buf[axis == 0 ? B3_U : (axis == 1 ? B3_V : B3_W)];
+    if (axis != 2 && c->opt_gen2) {
+        // x- and y-sweeps on the second-generation 2-D x-sweep kernel (marching axis strided, columns = k): a batch of 2-D
+        // problems -- the j-lines marching i (x), or the planes marching j (y)
+        Grid g2{};
+        g2.ny = c->g.nz;
+        const int nstrips = cdiv(c->g.nz + 1, 64), rpc = 48;
+        int r0, r1, nbatch, blo, bhi;
+        long long bstride, boff;
+        if (axis == 0) {
+            g2.nx = c->g.nx; g2.gi0 = c->g.gi0; g2.nrows = c->g.nrows; g2.pitch = (int)c->g.pj;
+            r0 = c->in_a; r1 = c->in_b;
+            nbatch = c->g.ny + 2; bstride = c->g.pk; boff = 0; blo = 1; bhi = c->g.ny;
+        } else {
+            g2.nx = c->g.ny; g2.gi0 = 0; g2.nrows = c->g.ny + 2; g2.pitch = c->g.pk;
+            r0 = 1; r1 = c->g.ny;
+            nbatch = c->all_b - c->all_a + 1; bstride = c->g.pj; boff = (long long)c->all_a * c->g.pj;
+            blo = std::max(0, 1 - (c->g.gi0 + c->all_a)); bhi = c->g.nx - (c->g.gi0 + c->all_a);
+        }
+        const int nitems = nstrips * nbatch * cdiv(r1 - r0 + 1, rpc);
+        WorkQueue wq{c->diag->wq, nitems};
+#define FX3 g2, c->fct[axis], wq, c->F() + boff, vel + boff, c->F_alt() + boff, r0, r1, rpc, nstrips, nbatch, bstride, blo, bhi
+        if (post) launch_queue3(c, k_fct_x5<true, 2, FctOps3, true>, 2, kFctXWarps, nitems, FX3);
+        else launch_queue3(c, k_fct_x5<false, 2, FctOps3, true>, 3, kFctXWarps, nitems, FX3);
+#undef FX3
+        c->F_cur ^= 1;
+        return launch_ok("k_fct_x5 (3-D)");
+    }
     if (axis == 0) {
         const int planes = c->in_b - c->in_a + 1, per = 64;
         dim3 grid(cdiv(c->g.nz + 2, kB3), c->g.ny + 2, cdiv(planes, per));
@@ -288,15 +332,8 @@ static int run3_fct(Vof3Ctx* c, int axis, bool post) {
         const int nstrips = cdiv(c->g.nz + 1, kFctYValid), rpw = 16;
         const int nitems = nstrips * cdiv(r1 - r0 + 1, rpw);
         WorkQueue wq{c->diag->wq, nitems};
-        if (!c->resident_y5[post ? 1 : 0]) {
-            int nb = 0;
-            auto kern = post ? k_fct_y5<true, FctOps3, true> : k_fct_y5<false, FctOps3, true>;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * kFctYWarps, 0) != cudaSuccess) nb = 1;
-            c->resident_y5[post ? 1 : 0] = std::max(1, nb) * c->sm_count;
-        }
-        const int blocks = std::min(cdiv(nitems, kFctYWarps), c->resident_y5[post ? 1 : 0]);
-        if (post) k_fct_y5<true, FctOps3, true><<<blocks, 32 * kFctYWarps, 0, c->stream>>>(g2, c->fct[2], wq, c->F(), vel, c->F_alt(), r0, r1, rpw, nstrips, rpp);
-        else k_fct_y5<false, FctOps3, true><<<blocks, 32 * kFctYWarps, 0, c->stream>>>(g2, c->fct[2], wq, c->F(), vel, c->F_alt(), r0, r1, rpw, nstrips, rpp);
+        if (post) launch_queue3(c, k_fct_y5<true, FctOps3, true>, 0, kFctYWarps, nitems, g2, c->fct[2], wq, c->F(), vel, c->F_alt(), r0, r1, rpw, nstrips, rpp);
+        else launch_queue3(c, k_fct_y5<false, FctOps3, true>, 1, kFctYWarps, nitems, g2, c->fct[2], wq, c->F(), vel, c->F_alt(), r0, r1, rpw, nstrips, rpp);
     } else {
         constexpr int TR = 8, TK = 128;
         const long long rows = (long long)(c->all_b - c->all_a + 1) * (c->g.ny + 2);
@@ -470,7 +507,12 @@ extern "C" int vof3d_halo_push(Vof3Ctx* c, int field, int side, float* peer_halo
 
 extern "C" int vof3d_set_option(Vof3Ctx* c, int option, int value) {
     if (!c) return fail(VOF_EINVAL, "null context");
-    if (option != VOF_OPT_ADAPTIVE) return fail(VOF_EINVAL, "3-D contexts know option VOF_OPT_ADAPTIVE only (got %d)", option);
+    if (option == VOF_OPT_CHUNK_CAP) {
+        if (value < 0) return fail(VOF_EINVAL, "chunk cap must be >= 0");
+        c->opt_jac_rows = value > 0 ? value : kJacRows3;
+        return VOF_OK;
+    }
+    if (option != VOF_OPT_ADAPTIVE) return fail(VOF_EINVAL, "3-D contexts know VOF_OPT_ADAPTIVE and VOF_OPT_CHUNK_CAP only (got %d)", option);
     if (value != 0 && value != 1) return fail(VOF_EINVAL, "adaptive must be 0 or 1");
     c->opt_gen2 = value;
     return VOF_OK;
