@@ -265,7 +265,11 @@ static int run3_project(Vof3Ctx* c, bool inl) {
     unsigned long long* cc = &c->diag->courant_count;
     CU(cudaMemsetAsync(cc, 0, sizeof(*cc), c->stream));
 #define P3 c->g, c->k, inl ? c->F() : c->buf[B3_RHO], c->p(), c->buf[B3_US], c->buf[B3_VS], c->buf[B3_WS], c->buf[B3_U], c->buf[B3_V], c->buf[B3_W], cc, a, b, kRows3, c->lo - c->g.gi0, c->hi - c->g.gi0
-    if (inl) k3_project<true><<<grid, kB3, 0, c->stream>>>(P3);
+    if (inl && c->opt_gen2) {
+        dim3 g5(cdiv(c->g.nz, 128), cdiv(c->g.ny, 4), cdiv(b - a + 1, kRows3));
+        k3_project5<<<g5, 128, 0, c->stream>>>(c->g, c->k, c->F(), c->p(), c->buf[B3_US], c->buf[B3_VS], c->buf[B3_WS], c->buf[B3_U], c->buf[B3_V],
+                                               c->buf[B3_W], cc, a, b, kRows3, c->lo - c->g.gi0, c->hi - c->g.gi0);
+    } else if (inl) k3_project<true><<<grid, kB3, 0, c->stream>>>(P3);
     else k3_project<false><<<grid, kB3, 0, c->stream>>>(P3);
 #undef P3
     return launch_ok("k3_project");

@@ -431,6 +431,109 @@ k3_project(Grid3 g, Consts3 c, const float* __restrict__ rhoF, const float* __re
     if (flags) atomicAdd(courant_count, (unsigned long long)flags);
 }
 
+// ---- update_uv, second generation: float4 lanes along k, a warp per j-line, 4 lines per block, marching i.  Everything
+// plane i+1 needs is requested while plane i is computed (the first-generation kernel was latency bound: every load
+// was issued where it was consumed); rho is evaluated once per cell and line instead of four times per cell; the
+// k-1 neighbours come from the adjacent lane.  Properties from F (the fused step); same expressions, same order.
+__global__ void __launch_bounds__(128)
+k3_project5(Grid3 g, Consts3 c, const float* __restrict__ F, const float* __restrict__ p, const float* __restrict__ us,
+            const float* __restrict__ vs, const float* __restrict__ ws, float* __restrict__ u, float* __restrict__ v,
+            float* __restrict__ w, unsigned long long* __restrict__ courant_count, int r0, int r1, int rows_per_block,
+            int own_a, int own_b) {
+    const int lane = threadIdx.x & 31;
+    const int j = 1 + blockIdx.y * 4 + (threadIdx.x >> 5);
+    if (j > g.ny) return;                                                 // warp-uniform
+    const int kl = 1 + (blockIdx.x * 32 + lane) * 4;
+    const bool active = kl <= g.nz;
+    const int ia = r0 + blockIdx.z * rows_per_block, ib = min(r1, ia + rows_per_block - 1);
+    if (ia > ib) return;
+    const size_t si = (size_t)g.pj, sj = (size_t)g.pk;
+    size_t o = (size_t)ia * si + (size_t)j * sj + kl;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto ld4 = [&](const float* b, size_t q, bool ok) { return ok ? *reinterpret_cast<const float4*>(b + q) : z4; };
+    const bool full = kl + 3 <= g.nz;                                     // all four columns interior
+    const bool edge = active && lane == 0;                                // reads column kl-1 itself
+    bool colin[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) colin[q] = kl + q <= g.nz;
+    auto rho4 = [&](float4 f, float (&r)[4]) { r[0] = rho3(f.x, c); r[1] = rho3(f.y, c); r[2] = rho3(f.z, c); r[3] = rho3(f.w, c); };
+    // plane ia-1: p and rho only
+    float pm[4], rm[4];
+    { const float4 t = ld4(p, o - si, active); pm[0] = t.x; pm[1] = t.y; pm[2] = t.z; pm[3] = t.w; rho4(ld4(F, o - si, active), rm); }
+    float4 p_n = ld4(p, o, active), F_n = ld4(F, o, active), us_n = ld4(us, o, active), vs_n = ld4(vs, o, active), ws_n = ld4(ws, o, active);
+    float4 pj_n = ld4(p, o - sj, active), Fj_n = ld4(F, o - sj, active);
+    float pe_n = edge ? p[o - 1] : 0.0f, Fe_n = edge ? F[o - 1] : 0.0f;
+    unsigned flags = 0;
+    for (int i = ia; i <= ib; ++i, o += si) {
+        const float4 p4 = p_n, F4 = F_n, us4 = us_n, vs4 = vs_n, ws4 = ws_n, pj4 = pj_n, Fj4 = Fj_n;
+        const float pe = pe_n, Fe = Fe_n;
+        if (i < ib) {
+            const size_t on = o + si;
+            p_n = ld4(p, on, active); F_n = ld4(F, on, active); us_n = ld4(us, on, active); vs_n = ld4(vs, on, active); ws_n = ld4(ws, on, active);
+            pj_n = ld4(p, on - sj, active); Fj_n = ld4(F, on - sj, active);
+            if (edge) { pe_n = p[on - 1]; Fe_n = F[on - 1]; }
+        }
+        const int gi = g.gi0 + i;
+        const bool own = i >= own_a && i <= own_b;
+        const float pc[4] = {p4.x, p4.y, p4.z, p4.w}, usv[4] = {us4.x, us4.y, us4.z, us4.w}, vsv[4] = {vs4.x, vs4.y, vs4.z, vs4.w};
+        const float wsv[4] = {ws4.x, ws4.y, ws4.z, ws4.w}, pj[4] = {pj4.x, pj4.y, pj4.z, pj4.w};
+        float rc[4], rj[4];
+        rho4(F4, rc);
+        rho4(Fj4, rj);
+        float p_l = __shfl_up_sync(0xffffffffu, pc[3], 1), r_l = __shfl_up_sync(0xffffffffu, rc[3], 1);
+        if (edge) { p_l = pe; r_l = rho3(Fe, c); }
+        if (active) {
+            float ou[4], ov[4], ow[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float ru = (rc[q] + rm[q]) * 0.5f;
+                ou[q] = usv[q] - ((c.dt / ru) * (pc[q] - pm[q])) * c.dxi;
+                const float rv = (rc[q] + rj[q]) * 0.5f;
+                ov[q] = vsv[q] - ((c.dt / rv) * (pc[q] - pj[q])) * c.dyi;
+                const float rw = (rc[q] + (q ? rc[q - 1] : r_l)) * 0.5f;
+                ow[q] = wsv[q] - ((c.dt / rw) * (pc[q] - (q ? pc[q - 1] : p_l))) * c.dzi;
+            }
+            const bool urow = gi >= 2 && gi <= g.nx, vrow = gi >= 1 && gi <= g.nx;
+            if (urow) {
+                if (full) *reinterpret_cast<float4*>(u + o) = make_float4(ou[0], ou[1], ou[2], ou[3]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (colin[q]) u[o + q] = ou[q];
+                }
+                if (own) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) flags += colin[q] && (ou[q] * c.dt > c.cflx);
+                }
+            }
+            if (vrow) {
+                if (j >= 2) {
+                    if (full) *reinterpret_cast<float4*>(v + o) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                    else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (colin[q]) v[o + q] = ov[q];
+                    }
+                    if (own) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) flags += colin[q] && (ov[q] * c.dt > c.cfly);
+                    }
+                }
+                if (full && kl >= 2) *reinterpret_cast<float4*>(w + o) = make_float4(ow[0], ow[1], ow[2], ow[3]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (colin[q] && kl + q >= 2) w[o + q] = ow[q];
+                }
+                if (own) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) flags += colin[q] && kl + q >= 2 && (ow[q] * c.dt > c.cflx);   // 0.25*dx, 3dvof.py:301
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { pm[q] = pc[q]; rm[q] = rc[q]; }
+    }
+    if (flags) atomicAdd(courant_count, (unsigned long long)flags);
+}
+
 // ---- FCT sweeps (3dvof.py:366-541) -----------------------------------------------------------------------------------
 struct Fct3C {
     float dt, dx, dy, dz, vol, dtd;   // dtd: dt*dy*dz | dt*dx*dz | dt*dx*dy by axis
