@@ -215,7 +215,11 @@ static int run3_advect(Vof3Ctx* c, bool inl) {
     const int a = std::max(c->in_a, 1), b = std::min(c->in_b, c->g.nrows - 2);
     dim3 grid = grid_jk(c, c->g.nz, c->g.ny, b - a + 1, kRows3);
 #define A3 c->g, c->k, c->buf[B3_U], c->buf[B3_V], c->buf[B3_W], c->F(), c->buf[B3_RHO], c->buf[B3_NU], c->buf[B3_US], c->buf[B3_VS], c->buf[B3_WS], a, b, kRows3
-    if (inl) k3_advect<true><<<grid, kB3, 0, c->stream>>>(A3);
+    if (inl && c->opt_gen2) {
+        dim3 g5(cdiv(c->g.nz, 128), cdiv(c->g.ny, 4), cdiv(b - a + 1, kRows3));
+        k3_advect5<<<g5, 128, 0, c->stream>>>(c->g, c->k, c->buf[B3_U], c->buf[B3_V], c->buf[B3_W], c->F(), c->buf[B3_US], c->buf[B3_VS], c->buf[B3_WS],
+                                              a, b, kRows3);
+    } else if (inl) k3_advect<true><<<grid, kB3, 0, c->stream>>>(A3);
     else k3_advect<false><<<grid, kB3, 0, c->stream>>>(A3);
 #undef A3
     return launch_ok("k3_advect");

@@ -104,6 +104,128 @@ k3_advect(Grid3 g, Consts3 c, const float* __restrict__ u, const float* __restri
     (void)rho;
 }
 
+// ---- advect_upwind, second generation: float4 lanes along k, a warp per j-line, 4 lines per block, marching i.  The
+// first-generation kernel issues ~28 scalar loads per cell (302 instructions per cell, ncu); here a lane loads ten float4
+// per plane step for its 4 cells, the i-neighbours roll through registers and the k-neighbours come from the adjacent
+// lanes.  Properties from F (the fused step); expressions and their order are those of k3_advect / 3dvof.py:207-258.
+__global__ void __launch_bounds__(128)
+k3_advect5(Grid3 g, Consts3 c, const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ w,
+           const float* __restrict__ F, float* __restrict__ us, float* __restrict__ vs, float* __restrict__ ws,
+           int r0, int r1, int rows_per_block) {
+    const int lane = threadIdx.x & 31;
+    const int j = 1 + blockIdx.y * 4 + (threadIdx.x >> 5);
+    if (j > g.ny) return;                                                 // warp-uniform
+    const int kl = 1 + (blockIdx.x * 32 + lane) * 4;
+    const bool active = kl <= g.nz;
+    const int ia = r0 + blockIdx.z * rows_per_block, ib = min(r1, ia + rows_per_block - 1);
+    if (ia > ib) return;
+    const size_t si = (size_t)g.pj, sj = (size_t)g.pk;
+    size_t o = (size_t)ia * si + (size_t)j * sj + kl;
+    struct R4 { float x[4]; };
+    auto ld = [&](const float* b, size_t q) { R4 r; const float4 t = active ? *reinterpret_cast<const float4*>(b + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                              r.x[0] = t.x; r.x[1] = t.y; r.x[2] = t.z; r.x[3] = t.w; return r; };
+    const bool ledge = active && lane == 0;                               // reads column kl-1 itself
+    const bool redge = active && (lane == 31 || kl + 4 == g.nz + 1);      // reads column kl+4 itself
+    auto left = [&](const R4& r, const float* b, size_t q) { float x = __shfl_up_sync(0xffffffffu, r.x[3], 1); if (ledge) x = b[q - 1]; return x; };
+    auto right = [&](const R4& r, const float* b, size_t q) { float x = __shfl_down_sync(0xffffffffu, r.x[0], 1); if (redge) x = b[q + 4]; return x; };
+    const bool full = kl + 3 <= g.nz;
+    bool colin[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) colin[q] = kl + q <= g.nz;
+    // rolled along i: planes i-1 and i of the line j, u of the line j-1 (plane i), v of the line j+1 (plane i-1)
+    R4 u_m = ld(u, o - si), u_c = ld(u, o), u_cjm = ld(u, o - sj);
+    R4 v_m = ld(v, o - si), v_c = ld(v, o), v_mjp = ld(v, o - si + sj);
+    R4 w_m = ld(w, o - si), w_c = ld(w, o);
+    for (int i = ia; i <= ib; ++i, o += si) {
+        const int gi = g.gi0 + i;
+        const R4 u_p = ld(u, o + si), u_pjm = ld(u, o + si - sj), v_p = ld(v, o + si), w_p = ld(w, o + si);
+        const R4 u_jp = ld(u, o + sj), v_jm = ld(v, o - sj), v_jp = ld(v, o + sj), w_jm = ld(w, o - sj), w_jp = ld(w, o + sj);
+        const R4 f_c = ld(F, o);
+        // k-neighbours (column kl-1 / kl+4) of the lines that need them
+        const float u_c_l = left(u_c, u, o), u_c_r = right(u_c, u, o), u_p_l = left(u_p, u, o + si);
+        const float v_c_l = left(v_c, v, o), v_c_r = right(v_c, v, o), v_jp_l = left(v_jp, v, o + sj);
+        const float w_c_l = left(w_c, w, o), w_c_r = right(w_c, w, o), w_m_r = right(w_m, w, o - si), w_jm_r = right(w_jm, w, o - sj);
+        if (active) {
+            float ou[4], ov[4], ow[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float nu_c = nu3(f_c.x[q], c);
+                const float uc = u_c.x[q], vc = v_c.x[q], wc = w_c.x[q];
+                const float ukm = q ? u_c.x[q - 1] : u_c_l, ukp = q < 3 ? u_c.x[q + 1] : u_c_r;
+                const float vkm = q ? v_c.x[q - 1] : v_c_l, vkp = q < 3 ? v_c.x[q + 1] : v_c_r;
+                const float wkm = q ? w_c.x[q - 1] : w_c_l, wkp = q < 3 ? w_c.x[q + 1] : w_c_r;
+                {   // 3dvof.py:210-225
+                    const float v_here = 0.25f * (((v_m.x[q] + v_mjp.x[q]) + vc) + v_jp.x[q]);
+                    const float w_here = 0.25f * (((w_m.x[q] + (q < 3 ? w_m.x[q + 1] : w_m_r)) + wc) + wkp);
+                    const float um = u_m.x[q], up = u_p.x[q], ujm = u_cjm.x[q], ujp = u_jp.x[q];
+                    const float dudx = uc > 0.0f ? (uc - um) * c.dxi : (up - uc) * c.dxi;
+                    const float dudy = v_here > 0.0f ? (uc - ujm) * c.dyi : (ujp - uc) * c.dyi;
+                    const float dudz = w_here > 0.0f ? (uc - ukm) * c.dzi : (ukp - uc) * c.dzi;
+                    float acc = (nu_c * ((um - 2.0f * uc) + up)) * c.dxi2;
+                    acc = acc + (nu_c * ((ujm - 2.0f * uc) + ujp)) * c.dyi2;
+                    acc = acc + (nu_c * ((ukm - 2.0f * uc) + ukp)) * c.dzi2;
+                    acc = acc - uc * dudx; acc = acc - v_here * dudy; acc = acc - w_here * dudz;
+                    acc = acc + c.gx;                                // + fx_kappa*2/(rho+rho) is +-0: kappa == 0
+                    ou[q] = uc + c.dt * acc;
+                }
+                {   // 3dvof.py:226-241
+                    const float u_here = 0.25f * (((u_cjm.x[q] + uc) + u_pjm.x[q]) + u_p.x[q]);
+                    const float w_here = 0.25f * ((((q < 3 ? w_jm.x[q + 1] : w_jm_r) + w_jm.x[q]) + wc) + wkp);
+                    const float vm = v_m.x[q], vp = v_p.x[q], vjm = v_jm.x[q], vjp = v_jp.x[q];
+                    const float dvdx = u_here > 0.0f ? (vc - vm) * c.dxi : (vp - vc) * c.dxi;
+                    const float dvdy = vc > 0.0f ? (vc - vjm) * c.dyi : (vjp - vc) * c.dyi;
+                    const float dvdz = w_here > 0.0f ? (vc - vkm) * c.dzi : (vkp - vc) * c.dzi;
+                    float acc = (nu_c * ((vm - 2.0f * vc) + vp)) * c.dxi2;
+                    acc = acc + (nu_c * ((vjm - 2.0f * vc) + vjp)) * c.dyi2;
+                    acc = acc + (nu_c * ((vkm - 2.0f * vc) + vkp)) * c.dzi2;
+                    acc = acc - u_here * dvdx; acc = acc - vc * dvdy; acc = acc - w_here * dvdz;
+                    acc = acc + c.gy;
+                    ov[q] = vc + c.dt * acc;
+                }
+                {   // 3dvof.py:242-258
+                    const float u_here = 0.25f * ((((q ? u_p.x[q - 1] : u_p_l) + ukm) + u_p.x[q]) + uc);
+                    const float v_here = 0.25f * ((((q ? v_jp.x[q - 1] : v_jp_l) + vkm) + vc) + v_jp.x[q]);
+                    const float wm = w_m.x[q], wp = w_p.x[q], wjm = w_jm.x[q], wjp = w_jp.x[q];
+                    const float dwdx = u_here > 0.0f ? (wc - wm) * c.dxi : (wp - wc) * c.dxi;
+                    const float dwdy = v_here > 0.0f ? (wc - wjm) * c.dyi : (wjp - wc) * c.dyi;
+                    const float dwdz = wc > 0.0f ? (wc - wkm) * c.dzi : (wkp - wc) * c.dzi;
+                    float acc = (nu_c * ((wm - 2.0f * wc) + wp)) * c.dxi2;
+                    acc = acc + (nu_c * ((wjm - 2.0f * wc) + wjp)) * c.dyi2;
+                    acc = acc + (nu_c * ((wkm - 2.0f * wc) + wkp)) * c.dzi2;
+                    acc = acc - u_here * dwdx; acc = acc - v_here * dwdy; acc = acc - wc * dwdz;
+                    acc = acc + c.gz;
+                    ow[q] = wc + c.dt * acc;
+                }
+            }
+            const bool irow = gi >= 1 && gi <= g.nx;
+            if (gi >= 2 && gi <= g.nx) {
+                if (full) *reinterpret_cast<float4*>(us + o) = make_float4(ou[0], ou[1], ou[2], ou[3]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (colin[q]) us[o + q] = ou[q];
+                }
+            }
+            if (irow && j >= 2) {
+                if (full) *reinterpret_cast<float4*>(vs + o) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (colin[q]) vs[o + q] = ov[q];
+                }
+            }
+            if (irow) {
+                if (full && kl >= 2) *reinterpret_cast<float4*>(ws + o) = make_float4(ow[0], ow[1], ow[2], ow[3]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (colin[q] && kl + q >= 2) ws[o + q] = ow[q];
+                }
+            }
+        }
+        u_m = u_c; u_c = u_p; u_cjm = u_pjm;
+        v_m = v_c; v_c = v_p; v_mjp = v_jp;
+        w_m = w_c; w_c = w_p;
+    }
+}
+
 // ---- set_BC (3dvof.py:141-190): three loops, launched in the reference's order ---------------------------------
 // face 0: j-faces over (i, k); 1: i-faces over (j, k); 2: k-faces over (i, j).  mask: 1 u, 2 v, 4 w, 8 F, 16 p, 32 rho
 __global__ void __launch_bounds__(kB3)
