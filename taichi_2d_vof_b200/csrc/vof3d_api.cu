@@ -239,7 +239,10 @@ static int run3_rhs(Vof3Ctx* c, bool inl) {
     ++c->launches;
     const int a = c->in_a, b = std::min(c->in_b, c->g.nrows - 2);
     dim3 grid = grid_jk(c, c->g.nz, c->g.ny, b - a + 1, kRows3);
-    if (inl) k3_rhs<true><<<grid, kB3, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[B3_US], c->buf[B3_VS], c->buf[B3_WS], c->buf[B3_RHS], a, b, kRows3);
+    if (inl && c->opt_gen2) {
+        dim3 g5(cdiv(c->g.nz, 128), cdiv(c->g.ny, 4), cdiv(b - a + 1, kRows3));
+        k3_rhs5<<<g5, 128, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[B3_US], c->buf[B3_VS], c->buf[B3_WS], c->buf[B3_RHS], a, b, kRows3);
+    } else if (inl) k3_rhs<true><<<grid, kB3, 0, c->stream>>>(c->g, c->k, c->F(), c->buf[B3_US], c->buf[B3_VS], c->buf[B3_WS], c->buf[B3_RHS], a, b, kRows3);
     else k3_rhs<false><<<grid, kB3, 0, c->stream>>>(c->g, c->k, c->buf[B3_RHO], c->buf[B3_US], c->buf[B3_VS], c->buf[B3_WS], c->buf[B3_RHS], a, b, kRows3);
     return launch_ok("k3_rhs");
 }

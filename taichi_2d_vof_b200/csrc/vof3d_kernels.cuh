@@ -294,6 +294,58 @@ k3_rhs(Grid3 g, Consts3 c, const float* __restrict__ rhoF, const float* __restri
     }
 }
 
+// Poisson rhs, second generation: float4 lanes along k, a warp per j-line, u* rolled along i, w*[k+1] from the adjacent
+// lane, everything of plane i+1 requested while plane i is computed.  rho from F (the fused step).
+__global__ void __launch_bounds__(128)
+k3_rhs5(Grid3 g, Consts3 c, const float* __restrict__ F, const float* __restrict__ us, const float* __restrict__ vs,
+        const float* __restrict__ ws, float* __restrict__ rhs, int r0, int r1, int rows_per_block) {
+    const int lane = threadIdx.x & 31;
+    const int j = 1 + blockIdx.y * 4 + (threadIdx.x >> 5);
+    if (j > g.ny) return;                                                 // warp-uniform
+    const int kl = 1 + (blockIdx.x * 32 + lane) * 4;
+    const bool active = kl <= g.nz;
+    const int ia = r0 + blockIdx.z * rows_per_block, ib = min(r1, ia + rows_per_block - 1);
+    if (ia > ib) return;
+    const size_t si = (size_t)g.pj, sj = (size_t)g.pk;
+    size_t o = (size_t)ia * si + (size_t)j * sj + kl;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto ld4 = [&](const float* b, size_t q) { return active ? *reinterpret_cast<const float4*>(b + q) : z4; };
+    const bool redge = active && (lane == 31 || kl + 4 == g.nz + 1);      // reads column kl+4 itself
+    const bool full = kl + 3 <= g.nz;
+    float4 us_c = ld4(us, o);
+    float4 us_n = ld4(us, o + si), vs_n = ld4(vs, o), vj_n = ld4(vs, o + sj), ws_n = ld4(ws, o), f_n = ld4(F, o);
+    float we_n = redge ? ws[o + 4] : 0.0f;
+    for (int i = ia; i <= ib; ++i, o += si) {
+        const float4 us_p = us_n, vs4 = vs_n, vj4 = vj_n, ws4 = ws_n, f4 = f_n;
+        const float we = we_n;
+        if (i < ib) {
+            const size_t on = o + si;
+            us_n = ld4(us, on + si); vs_n = ld4(vs, on); vj_n = ld4(vs, on + sj); ws_n = ld4(ws, on); f_n = ld4(F, on);
+            if (redge) we_n = ws[on + 4];
+        }
+        float w_r = __shfl_down_sync(0xffffffffu, ws4.x, 1);
+        if (redge) w_r = we;
+        if (active) {
+            const float uc[4] = {us_c.x, us_c.y, us_c.z, us_c.w}, up[4] = {us_p.x, us_p.y, us_p.z, us_p.w};
+            const float vc[4] = {vs4.x, vs4.y, vs4.z, vs4.w}, vp[4] = {vj4.x, vj4.y, vj4.z, vj4.w};
+            const float wc[4] = {ws4.x, ws4.y, ws4.z, ws4.w}, ff[4] = {f4.x, f4.y, f4.z, f4.w};
+            float out[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float r = rho3(ff[q], c);
+                const float wp = q < 3 ? wc[q + 1] : w_r;
+                out[q] = (r / c.dt) * (((up[q] - uc[q]) * c.dxi + (vp[q] - vc[q]) * c.dyi) + (wp - wc[q]) * c.dzi);
+            }
+            if (full) *reinterpret_cast<float4*>(rhs + o) = make_float4(out[0], out[1], out[2], out[3]);
+            else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (kl + q <= g.nz) rhs[o + q] = out[q];
+            }
+        }
+        us_c = us_p;
+    }
+}
+
 // ---- solve_p_jacobi (3dvof.py:261-283): one sweep p -> pn; non-interior cells are copied -----------------------
 // RHS_MODE 0: hoisted rhs; 1: recomputed from the rho array (the reference's structure)
 template <int RHS_MODE>
