@@ -33,6 +33,7 @@ struct Vof3Ctx {
     long long launches;
     int sm_count, resident[8];  // resident blocks (whole device) of the queue-scheduled kernels, by variant
     int opt_jac_rows;          // planes one block of k3_jacobi5 marches
+    bool bc_clean;             // every ghost cell is what set_BC would write now (true after a whole step; any other writer clears it)
     int opt_gen2;              // 1 (default): second-generation kernels, 0: first generation (same bits)
     float* F() { return buf[F_cur ? B3_F1 : B3_F0]; }
     float* F_alt() { return buf[F_cur ? B3_F0 : B3_F1]; }
@@ -370,7 +371,7 @@ static void order3(int istep, int (&o)[3]) {   // 3dvof.py:351-363
 
 // ------------------------------------------------------------------------------------ entries
 extern "C" int vof3d_set_init_F(Vof3Ctx* c, int ic) {
-    CHECK_CTX(c);
+    CHECK_CTX(c); c->bc_clean = false;
     if (ic < 1 || ic > 3) return fail(VOF_EINVAL, "ic must be 1, 2 or 3 (got %d)", ic);
     if (ic != 1) return VOF_OK;   // 3dvof.py:126-138: -ic 2/3 are accepted and leave F == 0
     ++c->launches;
@@ -379,11 +380,11 @@ extern "C" int vof3d_set_init_F(Vof3Ctx* c, int ic) {
         c->g, (float)(c->P.Lx / 3), (float)(c->P.Ly / 2), (float)(c->P.Lz / 3), c->xs, c->ys, c->zs, c->F(), c->all_a, c->all_b);
     return launch_ok("k3_set_init_F");
 }
-extern "C" int vof3d_set_BC(Vof3Ctx* c) { CHECK_CTX(c); return run3_set_bc(c, 63u); }
-extern "C" int vof3d_cal_nu_rho(Vof3Ctx* c) { CHECK_CTX(c); return run3_cal_nu_rho(c); }
-extern "C" int vof3d_advect_upwind(Vof3Ctx* c) { CHECK_CTX(c); return run3_advect(c, false); }
+extern "C" int vof3d_set_BC(Vof3Ctx* c) { CHECK_CTX(c); c->bc_clean = false; return run3_set_bc(c, 63u); }
+extern "C" int vof3d_cal_nu_rho(Vof3Ctx* c) { CHECK_CTX(c); c->bc_clean = false; return run3_cal_nu_rho(c); }
+extern "C" int vof3d_advect_upwind(Vof3Ctx* c) { CHECK_CTX(c); c->bc_clean = false; return run3_advect(c, false); }
 extern "C" int vof3d_solve_p_jacobi(Vof3Ctx* c, int nsweeps) {
-    CHECK_CTX(c);
+    CHECK_CTX(c); c->bc_clean = false;
     if (nsweeps < 0) return fail(VOF_EINVAL, "nsweeps must be >= 0");
     if (nsweeps == 1) return run3_jacobi(c, 1);
     if (nsweeps == 0) return VOF_OK;
@@ -391,17 +392,17 @@ extern "C" int vof3d_solve_p_jacobi(Vof3Ctx* c, int nsweeps) {
     for (int s = 0; s < nsweeps; ++s) TRY(run3_jacobi(c, 0));
     return VOF_OK;
 }
-extern "C" int vof3d_update_uv(Vof3Ctx* c) { CHECK_CTX(c); return run3_project(c, false); }
-extern "C" int vof3d_fct_x_sweep(Vof3Ctx* c) { CHECK_CTX(c); return run3_fct(c, 0, false); }
-extern "C" int vof3d_fct_y_sweep(Vof3Ctx* c) { CHECK_CTX(c); return run3_fct(c, 1, false); }
-extern "C" int vof3d_fct_z_sweep(Vof3Ctx* c) { CHECK_CTX(c); return run3_fct(c, 2, false); }
+extern "C" int vof3d_update_uv(Vof3Ctx* c) { CHECK_CTX(c); c->bc_clean = false; return run3_project(c, false); }
+extern "C" int vof3d_fct_x_sweep(Vof3Ctx* c) { CHECK_CTX(c); c->bc_clean = false; return run3_fct(c, 0, false); }
+extern "C" int vof3d_fct_y_sweep(Vof3Ctx* c) { CHECK_CTX(c); c->bc_clean = false; return run3_fct(c, 1, false); }
+extern "C" int vof3d_fct_z_sweep(Vof3Ctx* c) { CHECK_CTX(c); c->bc_clean = false; return run3_fct(c, 2, false); }
 extern "C" int vof3d_solve_VOF_rudman(Vof3Ctx* c, int istep) {
-    CHECK_CTX(c);
+    CHECK_CTX(c); c->bc_clean = false;
     int o[3]; order3(istep, o);
     for (int q = 0; q < 3; ++q) TRY(run3_fct(c, o[q], false));
     return VOF_OK;
 }
-extern "C" int vof3d_post_process_f(Vof3Ctx* c) { CHECK_CTX(c); return run3_post(c); }
+extern "C" int vof3d_post_process_f(Vof3Ctx* c) { CHECK_CTX(c); c->bc_clean = false; return run3_post(c); }
 
 extern "C" int vof3d_step(Vof3Ctx* c, int istep, unsigned flags) {
     CHECK_CTX(c);
@@ -417,19 +418,27 @@ extern "C" int vof3d_step(Vof3Ctx* c, int istep, unsigned flags) {
         for (int q = 0; q < 3; ++q) TRY(run3_fct(c, o[q], false));
         TRY(run3_post(c));
         TRY(run3_set_bc(c, 63u));
+        c->bc_clean = true;
         return VOF_OK;
     }
     const bool props = (flags & VOF_STEP_MATERIALIZE_PROPS) != 0;
     const unsigned mask = props ? 63u : 31u;
+    // set_BC is idempotent per field: a field whose interior has not changed since its ghosts were last filled keeps
+    // them.  Inside one step only u, v, w, p change before the 2nd call and only F before the 3rd, and the 1st call
+    // (after the predictor, which writes u*, v*, w* only) finds everything as the previous step's last call left it.
+    // Full-domain contexts only (halo planes of a slab are written from outside), never with materialised rho, and
+    // only while nothing but whole steps has touched the fields (bc_clean).
+    const bool lean_bc = c->opt_gen2 && !props && c->lo == 1 && c->hi == c->g.nx;   // the whole domain in one context
     if (props) TRY(run3_cal_nu_rho(c));
     TRY(run3_advect(c, true));
-    TRY(run3_set_bc(c, mask));
+    if (!(lean_bc && c->bc_clean)) TRY(run3_set_bc(c, mask));
     TRY(run3_rhs(c, true));
     for (int s = 0; s < c->P.n_jacobi; ++s) TRY(run3_jacobi(c, 0));
     TRY(run3_project(c, true));
-    TRY(run3_set_bc(c, mask));
+    TRY(run3_set_bc(c, lean_bc ? (1u | 2u | 4u | 16u) : mask));
     for (int q = 0; q < 3; ++q) TRY(run3_fct(c, o[q], q == 2));   // post_process_f fused into the last sweep
-    TRY(run3_set_bc(c, mask));
+    TRY(run3_set_bc(c, lean_bc ? 8u : mask));
+    c->bc_clean = true;
     return VOF_OK;
 }
 
@@ -449,7 +458,7 @@ static float* field3(Vof3Ctx* c, int f) {
     return nullptr;
 }
 extern "C" int vof3d_field_ptr(Vof3Ctx* c, int field, float** dev, int64_t* pitch_k, int64_t* pitch_j, int64_t* planes) {
-    CHECK_CTX(c);
+    CHECK_CTX(c); c->bc_clean = false;
     float* d = field3(c, field);
     if (!d) return fail(VOF_EINVAL, "unknown 3-D field id %d", field);
     if (dev) *dev = d;
@@ -469,7 +478,7 @@ extern "C" int vof3d_field_get(Vof3Ctx* c, int field, float* host_dst) {
     return VOF_OK;
 }
 extern "C" int vof3d_field_set(Vof3Ctx* c, int field, const float* host_src) {
-    CHECK_CTX(c);
+    CHECK_CTX(c); c->bc_clean = false;
     float* d = field3(c, field);
     if (!d || !host_src) return fail(VOF_EINVAL, "bad field id %d or null source", field);
     CU(cudaSetDevice(c->device));
@@ -496,7 +505,7 @@ extern "C" int vof3d_diagnostics(Vof3Ctx* c, double* mass, float* max_cfl, int64
 
 // halo planes are contiguous: `halo` whole i-planes = halo * pj floats per field per side
 extern "C" int vof3d_halo_ptr(Vof3Ctx* c, int field, int side, int send, float** dev, int64_t* count) {
-    CHECK_CTX(c);
+    CHECK_CTX(c); c->bc_clean = false;
     float* d = field3(c, field);
     if (!d || (side != 0 && side != 1)) return fail(VOF_EINVAL, "bad field id %d or side %d", field, side);
     if ((side == 0 && c->has_lo) || (side == 1 && c->has_hi)) return fail(VOF_ESTATE, "side %d of this context is a physical wall", side);
@@ -507,7 +516,7 @@ extern "C" int vof3d_halo_ptr(Vof3Ctx* c, int field, int side, int send, float**
     return VOF_OK;
 }
 extern "C" int vof3d_halo_push(Vof3Ctx* c, int field, int side, float* peer_halo_dst) {
-    CHECK_CTX(c);
+    CHECK_CTX(c); c->bc_clean = false;
     float* src; int64_t n;
     TRY(vof3d_halo_ptr(c, field, side, 1, &src, &n));
     if (!peer_halo_dst) return fail(VOF_EINVAL, "null peer destination");

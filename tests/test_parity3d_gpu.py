@@ -121,3 +121,22 @@ def test_generations_identical_3d(built_lib):
         out.append({k: getattr(s, k).to_numpy() for k in CORE})
     for k in CORE:
         assert out[0][k].tobytes() == out[1][k].tobytes(), f"field {k} differs between the kernel generations"
+
+
+def test_lean_bc_tracks_outside_writers_3d(built_lib):
+    """The fused 3-D step skips set_BC on fields whose interior has not changed since their ghosts were filled; any writer
+    other than a whole step (field_set, single entries) must bring the full calls back.  Interleave both with the oracle."""
+    rng = np.random.default_rng(11)
+    P = Vof3DParams(nx=16, ny=14, nz=36, Lx=0.008, Ly=0.007, Lz=0.018)
+    o = Vof3DOracle(P); o.set_init_F(1)
+    s = _solver(P); s.set_init_F(1)
+    for step in range(1, 10):
+        if step == 4:      # overwrite u (ghosts included) from outside: the next step's first set_BC matters again
+            un = (rng.random(o.u.shape, dtype=np.float32) - 0.5) * 0.1
+            o.u[...] = un; s.u.from_numpy(un)
+        if step == 7:      # a single entry between steps
+            o.post_process_f(); s.post_process_f()
+            Fn = o.F.copy(); Fn[0, :, :] = 0.25; Fn[:, :, 0] = 0.5   # and ghosts that set_BC must repair
+            o.F[...] = Fn; s.F.from_numpy(Fn)
+        o.step(); s.step()
+        _same(s, o, CORE, f"lean-bc step {step}")
