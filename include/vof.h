@@ -173,6 +173,7 @@ enum {
     VOF_OPT_JACOBI_TB = 0,    /* <= 5 sweeps per HBM pass: 0 never, 1 when p/rhs exceed L2 (default), 2 always */
     VOF_OPT_FCT_X_COLS = 1,   /* columns per lane of the x-sweep kernel: 2 (default) or 4 */
     VOF_OPT_ADVECT_COLS = 2,  /* columns per lane of the momentum predictor: 2 (default) or 4 */
+    VOF_OPT_JACOBI_MAXT = 5,  /* sweeps per HBM pass of the blocked Jacobi at most: 5 (default; 10 sweeps = 5 + 5) .. 1 */
     VOF_OPT_CHUNK_CAP = 4,    /* > 0: cap on the rows one warp marches per work item in the streaming kernels (tuning) */
     VOF_OPT_ADAPTIVE = 3      /* 1 (default): interface-adaptive FCT / curvature kernels -- bulk rows where F is uniform
                                  across a warp's strip take an exact short-cut, the x-sweep streams rows through a

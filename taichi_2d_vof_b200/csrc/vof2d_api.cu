@@ -69,6 +69,7 @@ struct VofCtx {
     JacTB jac;                 // constants of the temporally blocked Jacobi
     int jac_resident_warps[6]; // warps of k_jacobi_tb<T> resident on the whole GPU, by T
     int opt_jacobi_tb;         // 1: temporal blocking (default), 0: one launch per sweep
+    int opt_jacobi_maxt;       // sweeps per HBM pass at most (5: 10 sweeps = 5 + 5; 4: 4 + 3 + 3 with narrower strip margins)
     int opt_fct_x_cols;        // columns per lane of the x-sweep (2 or 4)
     int opt_advect_cols;       // columns per lane of the momentum predictor (2 or 4)
     int resident[16];          // resident blocks (whole device) of the persistent streaming kernels, by variant; 0 = not asked yet
@@ -208,6 +209,7 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     }
     c->mom.k = k; c->mom.d_dx = make_const_div(k.dx); c->mom.d_dy = make_const_div(k.dy); c->mom.fast_div_ok = 0;
     c->opt_jacobi_tb = 1;
+    c->opt_jacobi_maxt = 5;
     c->opt_fct_x_cols = 2;
     c->opt_advect_cols = 2;
     c->opt_adaptive = 1;
@@ -470,7 +472,7 @@ static int launch_jacobi_tb(VofCtx* c, const float* pin, float* pout) {
         c->jac_resident_warps[T] = std::max(1, nb) * kJacWarpsPerBlock * c->sm_count;
     }
     JacSched sc;
-    sc.nstrips = cdiv(c->g.ny, kJacStripValid);
+    sc.nstrips = cdiv(c->g.ny, JacStrip<T>::valid);
     // items small enough that the queue balances data-dependent costs (several items per resident warp),
     // large enough that the 2T warm-up rows of an item stay a small fraction
     sc.rpc = std::min(rows, std::max(16 * T, 48));
@@ -496,7 +498,7 @@ static bool use_jacobi_tb(const VofCtx* c) {
 
 // nsweeps sweeps from the hoisted rhs, at most 5 per HBM pass; `frame`: keep ghost cells of p exact
 static int run_jacobi_tb(VofCtx* c, int nsweeps, bool frame) {
-    const int npass = cdiv(nsweeps, 5);
+    const int npass = cdiv(nsweeps, c->opt_jacobi_maxt);
     const int base = nsweeps / npass, extra = nsweeps % npass;
     for (int k = 0; k < npass; ++k) {
         const int T = base + (k < extra ? 1 : 0);
@@ -1008,6 +1010,7 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
     switch (option) {
         case VOF_OPT_JACOBI_TB: if (value < 0 || value > 2) return fail(VOF_EINVAL, "jacobi_tb must be 0, 1 or 2"); c->opt_jacobi_tb = value; break;
         case VOF_OPT_ADVECT_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "advect columns per lane must be 2 or 4"); c->opt_advect_cols = value; break;
+        case VOF_OPT_JACOBI_MAXT: if (value < 1 || value > 5) return fail(VOF_EINVAL, "jacobi sweeps per pass must be 1..5"); c->opt_jacobi_maxt = value; break;
         case VOF_OPT_CHUNK_CAP: if (value < 0) return fail(VOF_EINVAL, "chunk cap must be >= 0"); c->opt_chunk_cap = value; break;
         case VOF_OPT_ADAPTIVE: if (value != 0 && value != 1) return fail(VOF_EINVAL, "adaptive must be 0 or 1"); c->opt_adaptive = value; break;
         case VOF_OPT_FCT_X_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "fct_x columns per lane must be 2 or 4"); c->opt_fct_x_cols = value; break;

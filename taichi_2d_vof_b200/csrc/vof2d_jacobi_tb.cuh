@@ -8,7 +8,7 @@
 //     (slots rotate with period 3, so the row loop is unrolled by 3 and rows are never moved);
 //   * j-neighbours inside a row come from the adjacent lanes with two shuffles per row per sweep;
 //   * a strip loses one column per sweep at each edge, so strips overlap by 2 x 8 columns
-//     (112 of 128 columns are stored) and chunks by 2 x T rows -- redundant work instead of
+//     (112 of 128 columns are stored; 120 when T <= 4) and chunks by 2 x T rows -- redundant work instead of
 //     any inter-warp communication.
 // Walls are zeroed coefficients (2dvof.py:258-262).  Strips that touch no j-wall use literal
 // constants; the two edge strips carry per-lane coefficients (EDGE = true).  Rows that touch an
@@ -195,8 +195,11 @@ __device__ __forceinline__ void jac_step(JacPipe<T>& S, const JacEdge& E, const 
 }
 
 constexpr int kJacStripCols = 128;      // columns a warp loads
-constexpr int kJacStripMargin = 8;      // columns given up at each strip edge (>= T, multiple of 4)
-constexpr int kJacStripValid = kJacStripCols - 2 * kJacStripMargin;
+// columns given up at each strip edge: >= T (a strip loses one column per sweep), a multiple of 4 (float4 lanes)
+template <int T> struct JacStrip {
+    static constexpr int margin = T <= 4 ? 4 : 8;
+    static constexpr int valid = kJacStripCols - 2 * margin;
+};
 constexpr int kJacWarpsPerBlock = 4;
 
 struct JacSched {          // work item -> (strip, chunk); warps pull items from a global counter
@@ -210,7 +213,7 @@ __device__ __forceinline__ void jac_run(const Grid& g, const JacTB& jc, const fl
                                         const int lane) {
     const int jl = jstrip + 4 * lane;
     const bool active = jl <= g.ny + 1;                                // lanes past the right ghost column idle
-    const bool store_lane = active && lane >= kJacStripMargin / 4 && lane < 32 - kJacStripMargin / 4;
+    const bool store_lane = active && lane >= JacStrip<T>::margin / 4 && lane < 32 - JacStrip<T>::margin / 4;
     const int P = g.pitch, last = g.nrows - 1;
     const float* pc = p + jl;
     const float* rc = rhs + jl;
@@ -253,7 +256,7 @@ template <int T, bool FAST_DIV>
 __global__ void __launch_bounds__(32 * kJacWarpsPerBlock)
 k_jacobi_tb(Grid g, JacTB jc, JacSched sc, const float* __restrict__ p, float* __restrict__ pout,
             const float* __restrict__ rhs, int r0, int r1) {
-    static_assert(T >= 1 && T <= kJacStripMargin, "strip margin must cover the sweeps of one pass");
+    static_assert(T >= 1 && T <= JacStrip<T>::margin, "strip margin must cover the sweeps of one pass");
     const int lane = threadIdx.x & 31;
     const int nitems = sc.nstrips * sc.nchunks;
     // persistent warps + work queue: the cost of an item is data dependent (tiny numerators take the fp64
@@ -266,7 +269,7 @@ k_jacobi_tb(Grid g, JacTB jc, JacSched sc, const float* __restrict__ p, float* _
         const int strip = item % sc.nstrips, chunk = item / sc.nstrips;
         const int ra = r0 + chunk * sc.rpc;
         const int rb = min(r1, ra + sc.rpc - 1);
-        const int jstrip = 1 - kJacStripMargin + strip * kJacStripValid;   // == 1 (mod 4): float4-aligned
+        const int jstrip = 1 - JacStrip<T>::margin + strip * JacStrip<T>::valid;   // == 1 (mod 4): float4-aligned
         const bool strip_interior = jstrip >= 2 && jstrip + kJacStripCols - 1 <= g.ny - 1;
         // every row the pipeline touches (ra - T .. rb + T, minus the sweeps' skew) strictly inside the i-walls?
         const bool wallrows = g.gi0 + ra - T - T < 2 || g.gi0 + rb + T > g.nx - 1;
