@@ -338,10 +338,13 @@ struct Span {
 };
 
 // Rows marched by one warp / block of the streaming kernels.  Long chunks amortise the warm-up rows that a chunk
-// re-reads, but a grid needs ~16 resident warps per SM to hide latency: on big grids the cap `max_rows` applies,
-// on small ones the chunks shrink (down to `min_rows`) until there are enough of them.
+// re-reads, but a grid needs full SMs to hide latency (a first version aimed at 16 warps per SM and left 2048^2 at 64 %
+// of what short items reach): on big grids the cap `max_rows` applies,
+// on small ones the chunks shrink (down to `min_rows`) until there are enough of them.  Small and medium grids are
+// latency bound -- a step is ~19 dependent kernels, each a serial march over its rows -- so short items win there even
+// when the warm-up rows double the work (200^2: 7.1k -> 10.2k steps/s, 1024^2: 4.6k -> 7.5k with 4-row items).
 static int chunk_rows(const VofCtx* c, int rows, int columns_of_units, int min_rows, int max_rows, int units_per_warp = 1) {
-    const int target_warps = c->sm_count * 16;
+    const int target_warps = c->sm_count * 128;     // two full waves of 64 warps per SM
     const int warps_per_row_chunk = std::max(1, columns_of_units / units_per_warp);
     const int nch = std::max(1, cdiv(target_warps, warps_per_row_chunk));
     int r = cdiv(rows, nch);
@@ -394,7 +397,7 @@ static int run_kappa(VofCtx* c) {
     const int nstrips = cdiv(c->g.ny, kKapValid);
     // adaptive kernel: items come from a queue and bulk rows are nearly free, so short items (less tail behind the
     // few expensive interface items) cost little; first generation: long chunks amortise the 4 warm-up rows
-    const int rpc = c->opt_adaptive ? chunk_rows(c, rows, nstrips, 16, 24) : chunk_rows(c, rows, nstrips, 16, 64);
+    const int rpc = c->opt_adaptive ? chunk_rows(c, rows, nstrips, 6, 24) : chunk_rows(c, rows, nstrips, 6, 64);
     dim3 grid(cdiv(nstrips * cdiv(rows, rpc), kKapWarps));
     if (c->opt_adaptive) {
         const int nitems = nstrips * cdiv(rows, rpc);
@@ -410,7 +413,7 @@ static int run_advect(VofCtx* c, bool inline_props) {
     const int rows = b - a + 1;
     const int nc = c->opt_advect_cols;
     const int nstrips = cdiv(c->g.ny, 32 * nc);
-    const int rpc = chunk_rows(c, rows, nstrips, 8, 64);
+    const int rpc = chunk_rows(c, rows, nstrips, 4, 64);
     dim3 grid(cdiv(nstrips * cdiv(rows, rpc), kMomWarps));
     if (c->opt_adaptive && inline_props && nc == 2) {
         const int nitems = nstrips * cdiv(rows, rpc);
@@ -529,7 +532,7 @@ static int run_project(VofCtx* c, bool inline_props) {
     const int a = std::max(c->in_a, 1), b = c->in_b;
     const int rows = b - a + 1;
     const int nstrips = cdiv(c->g.ny, 128);
-    const int rpc = chunk_rows(c, rows, nstrips, 8, 64);
+    const int rpc = chunk_rows(c, rows, nstrips, 4, 64);
     dim3 grid(cdiv(nstrips * cdiv(rows, rpc), kMomWarps));
     unsigned long long* cc = &c->diag->courant_count;
     CU(cudaMemsetAsync(cc, 0, sizeof(*cc), c->stream));
@@ -548,8 +551,8 @@ static int run_fct_x(VofCtx* c, bool post) {
     const int rows = c->in_b - c->in_a + 1;
     const int nc = c->opt_fct_x_cols;
     const int nstrips = cdiv(c->g.ny + 1, 32 * nc);
-    const int rpc = c->opt_adaptive ? chunk_rows(c, rows, nstrips, 24, 48)      // queue-scheduled: shorter items, less tail
-                                    : chunk_rows(c, rows, nstrips, 24, 96);     // 6 warm-up rows are re-read per chunk
+    const int rpc = c->opt_adaptive ? chunk_rows(c, rows, nstrips, 6, 48)       // queue-scheduled: shorter items, less tail
+                                    : chunk_rows(c, rows, nstrips, 6, 96);      // 6 warm-up rows are re-read per chunk
     const int nwarps = nstrips * cdiv(rows, rpc);
     dim3 grid(cdiv(nwarps, kFctXWarps));
 #define FXA c->g, c->fctx, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, rpc, nstrips
