@@ -477,8 +477,14 @@ static int launch_jacobi_tb(VofCtx* c, const float* pin, float* pout) {
     JacSched sc;
     sc.nstrips = cdiv(c->g.ny, JacStrip<T>::valid);
     // items small enough that the queue balances data-dependent costs (several items per resident warp),
-    // large enough that the 2T warm-up rows of an item stay a small fraction
-    sc.rpc = std::min(rows, std::max(16 * T, 48));
+    // large enough that the 2T warm-up rows of an item stay a small fraction; on grids too small to fill the
+    // device that way the items shrink (down to 4T rows: 1.5x the work, but every SM has some)
+    {
+        const int rpc_max = std::max(16 * T, 48), rpc_min = 4 * T;
+        const long long want_items = 2LL * c->jac_resident_warps[T];
+        const int fill = (int)std::min<long long>(rpc_max, (long long)rows * sc.nstrips / want_items);
+        sc.rpc = std::min(rows, std::max(rpc_min, fill));
+    }
     sc.nchunks = cdiv(rows, sc.rpc);
     sc.counter = &c->diag->queue;
     const int nitems = sc.nstrips * sc.nchunks;
