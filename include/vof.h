@@ -165,7 +165,7 @@ enum {
     VOF_K_FCT_X, VOF_K_FCT_Y, VOF_K_POST, VOF_K_HALO, VOF_K_COUNT
 };
 int64_t vof2d_launch_count(const VofCtx* c);
-int vof2d_profile(VofCtx* c, int enable);                 /* enable/disable; always resets the spans */
+int vof2d_profile(VofCtx* c, int enable);                 /* 0 off, 1 every launch, k > 1 the launches of every k-th vof2d_step; always resets the spans */
 int vof2d_profile_read(VofCtx* c, int kind, double* ms_total, int64_t* spans);  /* synchronous */
 
 /* tuning knobs for A/B measurements (defaults = fast paths; results are identical either way) */

@@ -82,7 +82,9 @@ struct VofCtx {
     int sm_count;
     // launch accounting + optional per-kernel-kind CUDA-event timing (vof2d_profile)
     long long launches;
-    bool profiling;
+    bool profiling;            // spans are recorded (and graph replay is off)
+    int prof_every, prof_count; // ... on every prof_every-th whole step only (sampling keeps the instrumentation out of the timing)
+    bool prof_now;
     std::vector<cudaEvent_t>* ev_pool;        // recycled events
     std::vector<ProfSpan>* spans;             // (kind, start, stop) recorded on c->stream
     float* F() { return buf[F_cur ? BUF_F1 : BUF_F0]; }
@@ -327,7 +329,7 @@ struct Span {
     VofCtx* c; int kind; cudaEvent_t b;
     Span(VofCtx* c_, int kind_, int nlaunch = 1) : c(c_), kind(kind_), b(nullptr) {
         c->launches += nlaunch;
-        if (!c->profiling) return;
+        if (!c->profiling || !c->prof_now) return;
         cudaEvent_t a;
         auto get = [&]() { cudaEvent_t e; if (!c->ev_pool->empty()) { e = c->ev_pool->back(); c->ev_pool->pop_back(); } else cudaEventCreate(&e); return e; };
         a = get(); b = get();
@@ -716,6 +718,7 @@ extern "C" int vof2d_interp_velocity(VofCtx* c, float* V_host) {
 // the loop body 2dvof.py:513-528
 // ------------------------------------------------------------------------------------
 static int step_impl(VofCtx* c, int istep, unsigned flags) {
+    if (c->profiling) c->prof_now = (c->prof_count++ % c->prof_every) == 0;
     if (flags & VOF_STEP_NO_FUSION) {
         TRY(run_cal_nu_rho(c));                                   // 513
         TRY(run_kappa(c));                                        // 514
@@ -991,6 +994,8 @@ extern "C" int vof2d_profile(VofCtx* c, int enable) {
     for (auto& sp : *c->spans) { c->ev_pool->push_back(sp.a); c->ev_pool->push_back(sp.b); }
     c->spans->clear();
     c->profiling = enable != 0;
+    c->prof_every = enable > 1 ? enable : 1;     // enable = k > 1: record the kernels of every k-th vof2d_step only
+    c->prof_count = 0; c->prof_now = true;
     return VOF_OK;
 }
 

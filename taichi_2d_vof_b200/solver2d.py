@@ -268,7 +268,8 @@ class VofSolver2D:
         return int(self._L.vof2d_launch_count(self._h))
 
     def profile(self, enable=True):
-        check(self._L.vof2d_profile(self._h, 1 if enable else 0))
+        """False / 0: off; True / 1: CUDA-event spans around every kernel; k > 1: around the kernels of every k-th step."""
+        check(self._L.vof2d_profile(self._h, int(enable)))
 
     def profile_read(self):
         """{kind: (total ms, launches)} of the spans recorded since profile(True)."""
