@@ -170,10 +170,11 @@ int vof2d_profile_read(VofCtx* c, int kind, double* ms_total, int64_t* spans);  
 
 /* tuning knobs for A/B measurements (defaults = fast paths; results are identical either way) */
 enum {
-    VOF_OPT_JACOBI_TB = 0,    /* <= 5 sweeps per HBM pass: 0 never, 1 when p/rhs exceed L2 (default), 2 always */
+    VOF_OPT_JACOBI_TB = 0,    /* blocked Jacobi (several sweeps per HBM pass): 0 never, 1 from ~1800^2 up (default), 2 always */
     VOF_OPT_FCT_X_COLS = 1,   /* columns per lane of the x-sweep kernel: 2 (default) or 4 */
     VOF_OPT_ADVECT_COLS = 2,  /* columns per lane of the momentum predictor: 2 (default) or 4 */
-    VOF_OPT_JACOBI_MAXT = 5,  /* sweeps per HBM pass of the blocked Jacobi at most: 5 (default; 10 sweeps = 5 + 5) .. 1 */
+    VOF_OPT_JACOBI_MAXT = 5,  /* sweeps per HBM pass of the blocked Jacobi at most: 0 (default) by grid size (3 up to ~5800^2,
+                                 5 beyond), or 1 .. 5 */
     VOF_OPT_CHUNK_CAP = 4,    /* > 0: cap on the rows one warp marches per work item in the streaming kernels (tuning) */
     VOF_OPT_ADAPTIVE = 3      /* 1 (default): interface-adaptive FCT / curvature kernels -- bulk rows where F is uniform
                                  across a warp's strip take an exact short-cut, the x-sweep streams rows through a

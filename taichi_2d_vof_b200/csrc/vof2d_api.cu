@@ -69,7 +69,7 @@ struct VofCtx {
     JacTB jac;                 // constants of the temporally blocked Jacobi
     int jac_resident_warps[6]; // warps of k_jacobi_tb<T> resident on the whole GPU, by T
     int opt_jacobi_tb;         // 1: temporal blocking (default), 0: one launch per sweep
-    int opt_jacobi_maxt;       // sweeps per HBM pass at most (5: 10 sweeps = 5 + 5; 4: 4 + 3 + 3 with narrower strip margins)
+    int opt_jacobi_maxt;       // sweeps per HBM pass at most: 0 = by grid size, else 1..5 (5: 10 sweeps = 5 + 5; 3: 3 + 3 + 2 + 2)
     int opt_fct_x_cols;        // columns per lane of the x-sweep (2 or 4)
     int opt_advect_cols;       // columns per lane of the momentum predictor (2 or 4)
     int resident[16];          // resident blocks (whole device) of the persistent streaming kernels, by variant; 0 = not asked yet
@@ -211,7 +211,7 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     }
     c->mom.k = k; c->mom.d_dx = make_const_div(k.dx); c->mom.d_dy = make_const_div(k.dy); c->mom.fast_div_ok = 0;
     c->opt_jacobi_tb = 1;
-    c->opt_jacobi_maxt = 5;
+    c->opt_jacobi_maxt = 0;
     c->opt_fct_x_cols = 2;
     c->opt_advect_cols = 2;
     c->opt_adaptive = 1;
@@ -497,19 +497,25 @@ static int launch_jacobi_tb(VofCtx* c, const float* pin, float* pout) {
     return launch_ok("k_jacobi_tb");
 }
 
-// Temporal blocking pays when p and rhs stream from HBM.  When they fit in the 126 MB L2 (<= ~2900^2 cells) the plain
-// one-sweep kernel runs from L2 and has far more parallelism than strips x chunks of a small grid.
-// opt_jacobi_tb: 0 = never, 1 = by grid size (default), 2 = always.
+// Blocked or single-sweep Jacobi, and how many sweeps per HBM pass (profiles/exp_tb_sizes.py, graph-replayed steps/s):
+// up to ~1500^2 the plain one-sweep kernel wins (it runs from L2 and has far more parallelism than strips x chunks of a
+// small grid); from 2048^2 the blocked kernel does, with at most 3 sweeps per pass while the three fields are a few
+// hundred MB (short register pipelines: the device is not full and per-warp latency counts), 5 beyond (HBM traffic counts).
+// opt_jacobi_tb: 0 = never, 1 = by grid size (default), 2 = always.  opt_jacobi_maxt: 0 = by grid size (default), 1..5.
+static double jacobi_field_mb(const VofCtx* c) { return 3.0 * (double)c->g.nrows * c->g.pitch * sizeof(float) / 1e6; }   // p, p', rhs
 static bool use_jacobi_tb(const VofCtx* c) {
     if (c->opt_jacobi_tb == 0) return false;
     if (c->opt_jacobi_tb == 2) return true;
-    const double mb = 3.0 * (double)c->g.nrows * c->g.pitch * sizeof(float) / 1e6;   // p, p', rhs
-    return mb > 100.0;
+    return jacobi_field_mb(c) > 40.0;
+}
+static int jacobi_max_sweeps(const VofCtx* c) {
+    if (c->opt_jacobi_maxt > 0) return c->opt_jacobi_maxt;
+    return jacobi_field_mb(c) > 400.0 ? 5 : 3;
 }
 
 // nsweeps sweeps from the hoisted rhs, at most 5 per HBM pass; `frame`: keep ghost cells of p exact
 static int run_jacobi_tb(VofCtx* c, int nsweeps, bool frame) {
-    const int npass = cdiv(nsweeps, c->opt_jacobi_maxt);
+    const int npass = cdiv(nsweeps, jacobi_max_sweeps(c));
     const int base = nsweeps / npass, extra = nsweeps % npass;
     for (int k = 0; k < npass; ++k) {
         const int T = base + (k < extra ? 1 : 0);
@@ -1024,7 +1030,7 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
     switch (option) {
         case VOF_OPT_JACOBI_TB: if (value < 0 || value > 2) return fail(VOF_EINVAL, "jacobi_tb must be 0, 1 or 2"); c->opt_jacobi_tb = value; break;
         case VOF_OPT_ADVECT_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "advect columns per lane must be 2 or 4"); c->opt_advect_cols = value; break;
-        case VOF_OPT_JACOBI_MAXT: if (value < 1 || value > 5) return fail(VOF_EINVAL, "jacobi sweeps per pass must be 1..5"); c->opt_jacobi_maxt = value; break;
+        case VOF_OPT_JACOBI_MAXT: if (value < 0 || value > 5) return fail(VOF_EINVAL, "jacobi sweeps per pass must be 0 (by grid size) or 1..5"); c->opt_jacobi_maxt = value; break;
         case VOF_OPT_CHUNK_CAP: if (value < 0) return fail(VOF_EINVAL, "chunk cap must be >= 0"); c->opt_chunk_cap = value; break;
         case VOF_OPT_ADAPTIVE: if (value != 0 && value != 1) return fail(VOF_EINVAL, "adaptive must be 0 or 1"); c->opt_adaptive = value; break;
         case VOF_OPT_FCT_X_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "fct_x columns per lane must be 2 or 4"); c->opt_fct_x_cols = value; break;
