@@ -73,6 +73,7 @@ struct VofCtx {
     int opt_fct_x_cols;        // columns per lane of the x-sweep (2 or 4)
     int opt_advect_cols;       // columns per lane of the momentum predictor (2 or 4)
     int resident[16];          // resident blocks (whole device) of the persistent streaming kernels, by variant; 0 = not asked yet
+    int opt_jac_rows;          // > 0: rows per item of the blocked Jacobi (default: max(16 T, 48))
     int opt_fit_rounds;        // 1: item sizes of the queue kernels are fitted to whole rounds of the resident warps (measured: no gain; default 0)
     int opt_chunk_cap;         // > 0: upper bound on the rows one warp marches in the streaming kernels (load-balance experiments)
     int opt_adaptive;          // 1: interface-adaptive kernels (warp-uniform bulk rows short-cut, cp.async ring), 0: first generation
@@ -500,7 +501,7 @@ static int launch_jacobi_tb(VofCtx* c, const float* pin, float* pout) {
     // large enough that the 2T warm-up rows of an item stay a small fraction; on grids too small to fill the
     // device that way the items shrink (down to 4T rows: 1.5x the work, but every SM has some)
     {
-        const int rpc_max = std::max(16 * T, 48), rpc_min = 4 * T;
+        const int rpc_max = c->opt_jac_rows > 0 ? c->opt_jac_rows : std::max(16 * T, 48), rpc_min = 4 * T;
         const long long want_items = 2LL * c->jac_resident_warps[T];
         const int fill = (int)std::min<long long>(rpc_max, (long long)rows * sc.nstrips / want_items);
         sc.rpc = std::min(rows, std::max(rpc_min, fill));
@@ -1062,6 +1063,7 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
         case VOF_OPT_JACOBI_TB: if (value < 0 || value > 2) return fail(VOF_EINVAL, "jacobi_tb must be 0, 1 or 2"); c->opt_jacobi_tb = value; break;
         case VOF_OPT_ADVECT_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "advect columns per lane must be 2 or 4"); c->opt_advect_cols = value; break;
         case VOF_OPT_JACOBI_MAXT: if (value < 0 || value > 5) return fail(VOF_EINVAL, "jacobi sweeps per pass must be 0 (by grid size) or 1..5"); c->opt_jacobi_maxt = value; break;
+        case VOF_OPT_JACOBI_ROWS: if (value < 0) return fail(VOF_EINVAL, "jacobi rows per item must be >= 0"); c->opt_jac_rows = value; break;
         case VOF_OPT_FIT_ROUNDS: if (value != 0 && value != 1) return fail(VOF_EINVAL, "fit_rounds must be 0 or 1"); c->opt_fit_rounds = value; break;
         case VOF_OPT_CHUNK_CAP: if (value < 0) return fail(VOF_EINVAL, "chunk cap must be >= 0"); c->opt_chunk_cap = value; break;
         case VOF_OPT_ADAPTIVE: if (value != 0 && value != 1) return fail(VOF_EINVAL, "adaptive must be 0 or 1"); c->opt_adaptive = value; break;
