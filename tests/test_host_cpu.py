@@ -133,3 +133,16 @@ def test_halo_exchange_gloo(world):
     import torch.multiprocessing as mp
     port = 29500 + (os.getpid() % 2000) + world
     mp.spawn(_slab_worker, args=(world, port, 16, 8), nprocs=world, join=True)
+
+
+def test_python_constants_match_header():
+    """Every VOF_OPT_* / VOF_VIEW_* / VOF_STEP_* constant the Python side uses has the value include/vof.h gives it."""
+    import re
+    from taichi_2d_vof_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "vof.h")).read()
+    found = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"\b(VOF_(?:OPT|VIEW)_[A-Z_0-9]+)\s*=\s*(\d+)", hdr))
+    assert {"VOF_OPT_JACOBI_TB", "VOF_OPT_ADAPTIVE", "VOF_OPT_CHUNK_CAP", "VOF_VIEW_VOF", "VOF_VIEW_VNORM"} <= set(found)
+    for name, value in found.items():
+        assert hasattr(_lib, name), f"{name} is missing from taichi_2d_vof_b200/_lib.py"
+        assert getattr(_lib, name) == value, f"{name}: header {value}, _lib.py {getattr(_lib, name)}"
+    assert len(set(v for k, v in found.items() if k.startswith("VOF_OPT_"))) == len([k for k in found if k.startswith("VOF_OPT_")]), "duplicate option ids"
