@@ -410,3 +410,22 @@ def test_display_kernels_refuse_slabs(built_lib):
     s = VofSolver2D(reference_params(nx=64, ny=64, slab=(1, 32), halo=16))
     with pytest.raises(Exception):
         s.get_vof_field()
+
+
+@pytest.mark.parametrize("n,adaptive", [(192, 1), (192, 0), (130, 1)])
+def test_kothe_rider_fct_matches_oracle(built_lib, n, adaptive):
+    """Pure FCT transport in the single-vortex field of the reference's test/forward_fct.py (Kothe-Rider), through the
+    production sweeps: the disc is stretched into a filament, so bulk strips, interface strips and every transition
+    between the adaptive kernels' modes occur in both sweep directions.  F identical to the oracle after every step."""
+    from test_oracle_cpu import kothe_rider_state
+    from taichi_2d_vof_b200 import _lib
+    P, o = kothe_rider_state(n)
+    s = _solver(P); s.set_option(_lib.VOF_OPT_ADAPTIVE, adaptive)
+    for k in ("F", "u", "v"):
+        getattr(s, k).from_numpy(getattr(o, k))
+    for step in range(60):
+        o.istep += 1; s.istep += 1
+        for name in ("solve_VOF_rudman", "post_process_f", "set_BC"):
+            getattr(o, name)(); getattr(s, name)()
+        a = s.F.to_numpy()
+        assert np.array_equal(a, o.F), f"step {step + 1}: F differs in {(a != o.F).sum()} cells"
