@@ -146,3 +146,33 @@ def test_python_constants_match_header():
         assert hasattr(_lib, name), f"{name} is missing from taichi_2d_vof_b200/_lib.py"
         assert getattr(_lib, name) == value, f"{name}: header {value}, _lib.py {getattr(_lib, name)}"
     assert len(set(v for k, v in found.items() if k.startswith("VOF_OPT_"))) == len([k for k in found if k.startswith("VOF_OPT_")]), "duplicate option ids"
+
+
+def test_driver3d_cli_matches_reference_flags():
+    from taichi_2d_vof_b200.driver3d import build_parser
+    p = build_parser()
+    a = p.parse_args([])
+    assert a.ic == 1 and a.s is False and (a.nx, a.ny, a.nz, a.jacobi, a.nstep) == (200, 200, 200, 10, 100)   # 3dvof.py:12-24, 590
+    a = p.parse_args(["-ic", "2", "-s"])
+    assert a.ic == 2 and a.s is True
+    with pytest.raises(SystemExit):
+        p.parse_args(["-ic", "0"])
+
+
+def test_vtr_export_roundtrip(tmp_path):
+    """The .vtr the 3-D driver writes in place of pyevtk.gridToVTK (3dvof.py:624-627): structure and payload."""
+    from taichi_2d_vof_b200.vtk import grid_to_vtk, read_vtr_arrays
+    rng = np.random.default_rng(0)
+    n = (5, 4, 7)
+    x, y, z = (np.linspace(0.0, 1.0, k).astype(np.float32) for k in n)
+    F = rng.random(n, dtype=np.float32)
+    fname = grid_to_vtk(str(tmp_path / "step-00100"), x, y, z, pointData={"VOF": F})
+    assert fname.endswith("step-00100.vtr")
+    text = open(fname, "rb").read()
+    assert b'type="RectilinearGrid"' in text and b'WholeExtent="0 4 0 3 0 6"' in text and b'Name="VOF"' in text
+    back = read_vtr_arrays(fname)
+    assert back["shape"] == n
+    assert np.array_equal(back["VOF"], F)                      # point (i, j, k) -> F[i, j, k], x fastest in the file
+    assert np.array_equal(back["x_coordinates"], x) and np.array_equal(back["z_coordinates"], z)
+    with pytest.raises(ValueError):
+        grid_to_vtk(str(tmp_path / "bad"), x, y, z, pointData={"VOF": F[:-1]})
