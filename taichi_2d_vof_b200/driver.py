@@ -36,6 +36,8 @@ def build_parser() -> argparse.ArgumentParser:
                    help="every nstep steps also run the GUI loop's display kernel of that view (2dvof.py:530-561: the 'v' key "
                         "cycles through these) and write output/%%06d-<view>.npy instead of painting a window")
     p.add_argument('--dump', type=str, default=None, help="write u,v,p,F (+istep) to this .npz at the end")
+    p.add_argument('--resume', type=str, default=None, help="continue from a --dump file (u, v, p, F and istep are the whole state: "
+                   "rho, nu, kappa, u*, v* are recomputed every step), bit-identical to an uninterrupted run")
     p.add_argument('--device', type=int, default=0)
     return p
 
@@ -63,7 +65,14 @@ def main(argv=None) -> int:
 
     s = VofSolver2D(P)
     nstep = args.nstep                      # 2dvof.py:497
-    s.set_init_F(initial_condition)         # 2dvof.py:498 (no set_BC before the first step)
+    if args.resume:
+        st = np.load(args.resume)
+        for k in ("u", "v", "p", "F"):
+            getattr(s, k).from_numpy(st[k])
+        s.istep = int(st["istep"])
+        print(f'>>> Resumed from {args.resume} at step {s.istep}')
+    else:
+        s.set_init_F(initial_condition)     # 2dvof.py:498 (no set_BC before the first step)
     os.makedirs('output', exist_ok=True)    # 2dvof.py:500
     t0 = time.perf_counter()
     try:

@@ -31,6 +31,7 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument('--no-export', action='store_true', help="skip the .vtr files")
     p.add_argument('--sequence', action='store_true', help="one C-ABI entry per reference kernel instead of the fused vof3d_step")
     p.add_argument('--dump', type=str, default=None, help="write u,v,w,p,F (+istep) to this .npz at the end")
+    p.add_argument('--resume', type=str, default=None, help="continue from a --dump file, bit-identical to an uninterrupted run")
     p.add_argument('--device', type=int, default=0)
     return p
 
@@ -55,7 +56,14 @@ def main(argv=None) -> int:
 
     s = VofSolver3D(P)
     nstep = args.nstep
-    s.set_init_F(args.ic)                   # 3dvof.py:591
+    if args.resume:
+        st = np.load(args.resume)
+        for k in ("u", "v", "w", "p", "F"):
+            getattr(s, k).from_numpy(st[k])
+        s.istep = int(st["istep"])
+        print(f'>>> Resumed from {args.resume} at step {s.istep}')
+    else:
+        s.set_init_F(args.ic)               # 3dvof.py:591
     os.makedirs('output', exist_ok=True)    # 3dvof.py:593
     t0 = time.perf_counter()
     try:
