@@ -224,3 +224,20 @@ def test_kothe_rider_transport_properties():
     assert np.isfinite(F).all() and F.min() >= 0.0 and F.max() <= 1.0
     assert abs(o.mass() - m0) / m0 < 5e-3            # conservative up to the clamps of var() (measured: -1.6e-3 after 80 steps)
     assert 0.002 < ((F > 0.01) & (F < 0.99)).mean() < 0.05   # a thin interface band: the disc has neither vanished nor smeared
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "vof3d_ic1_*.npz"))))
+def test_c_oracle_reproduces_golden_3d(path):
+    """The C twin of the 3-D oracle against the committed vectors (tests/golden/make_golden3d.py: NumPy oracle)."""
+    from oracle.c_oracle import Vof3DCOracle
+    from oracle.vof3d_oracle import Vof3DParams
+    g = np.load(path)
+    nx, ny, nz = (int(v) for v in g["params"][:3])
+    o = Vof3DCOracle(Vof3DParams(nx=nx, ny=ny, nz=nz, Lx=float(g["params"][3]), Ly=float(g["params"][4]), Lz=float(g["params"][5])))
+    o.set_init_F(1)
+    assert np.array_equal(o.F, g["F_init"])
+    for ck in (1, 3, 12):
+        o.run(ck - o.istep)
+        for k in ("u", "v", "w", "p", "F"):
+            assert np.array_equal(getattr(o, k), g[f"{k}_{ck}"]), f"{k} after {ck} steps"
+        assert abs(o.mass() - float(g[f"mass_{ck}"])) <= 1e-9 * float(g[f"mass_{ck}"])
