@@ -176,3 +176,22 @@ def test_vtr_export_roundtrip(tmp_path):
     assert np.array_equal(back["x_coordinates"], x) and np.array_equal(back["z_coordinates"], z)
     with pytest.raises(ValueError):
         grid_to_vtk(str(tmp_path / "bad"), x, y, z, pointData={"VOF": F[:-1]})
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the reference arm of the contract: the CPU restatement on the host cores) prints one
+    JSON line with the contract's keys; it runs without a GPU."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--n", "128"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Gcell-updates/s" and d["higher_is_better"] is True
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and d["dtype"] == "f32" and d["vs_baseline"] is None
