@@ -74,7 +74,7 @@ typedef struct VofParams {
     int32_t device;            /* CUDA device ordinal, -1 = current                           */
 } VofParams;
 
-#define VOF_SLAB_MIN_HALO 13   /* dependency radius of one whole step along i       */
+#define VOF_SLAB_MIN_HALO 15   /* n_jacobi + 5 at n_jacobi = 10: dependency radius of one step along i */
 
 /* vof2d_step / vof2d_run flags */
 #define VOF_STEP_MATERIALIZE_PROPS 1u  /* also write rho, nu (they are derived state: 2dvof.py:198-203) */
@@ -200,6 +200,9 @@ int vof2d_p2p_connect(VofCtx* c, int side, const void* handle64, void* same_proc
 int vof2d_p2p_arena(VofCtx* c, void** arena);
 int vof2d_halo_exchange_p2p(VofCtx* c);
 int vof2d_p2p_status(VofCtx* c, int* timed_out_epoch);   /* != 0: a wait gave up after 20 s (neighbour gone) */
+/* VOF_ESTATE (with the reason in vof_last_error) if any exchange so far timed out, or found a neighbour whose live
+ * F / p ping-pong buffers differ from this rank's (the push assumes lockstep).  Synchronises the stream. */
+int vof2d_p2p_check(VofCtx* c);
 
 /* =====================================================================================
  * 3-D twin: the loop body of 3dvof.py:598-623.  Fields are the reference's (nx+2, ny+2, nz+2) fp32

@@ -29,7 +29,7 @@ VOF_OPT_JACOBI_ROWS = 7
 VOF_VIEW_VOF, VOF_VIEW_U, VOF_VIEW_V, VOF_VIEW_VNORM = 0, 1, 2, 3
 VOF_STEP_MATERIALIZE_PROPS = 1
 VOF_STEP_NO_FUSION = 2
-VOF_SLAB_MIN_HALO = 13
+VOF_SLAB_MIN_HALO = 15
 
 
 class VofParams(C.Structure):
@@ -54,11 +54,12 @@ class VofError(RuntimeError):
 
 def build(force: bool = False) -> str:
     """Compile libvof.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "vof.h")]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if os.path.isfile(os.path.join(CSRC, f))]
+    srcs.append(os.path.join(_HERE, "..", "include", "vof.h"))
     stale = (not os.path.exists(LIB_PATH)
              or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs if os.path.exists(s)))
     if force or stale:
-        subprocess.run(["make", "-C", CSRC, "-s"] + (["-B"] if force else []), check=True)
+        subprocess.run(["make", "-C", CSRC, "-s", f"-j{min(8, os.cpu_count() or 1)}"] + (["-B"] if force else []), check=True)
     return LIB_PATH
 
 
@@ -116,6 +117,7 @@ SIGNATURES = {
     "vof2d_p2p_arena": (C.c_int, [_ctx, _P(C.c_void_p)]),
     "vof2d_halo_exchange_p2p": (C.c_int, [_ctx]),
     "vof2d_p2p_status": (C.c_int, [_ctx, _P(C.c_int)]),
+    "vof2d_p2p_check": (C.c_int, [_ctx]),
     # ---- 3-D
     "vof3d_arena_bytes": (C.c_size_t, [_P(VofParams)]),
     "vof3d_create": (C.c_int, [_P(VofParams), _P(_ctx)]),

@@ -1,5 +1,8 @@
 // libvof C ABI (include/vof.h) -- 2-D context, launches, field access, diagnostics.
 // Host code only decides ranges and launch shapes; all arithmetic is in vof2d_kernels.cuh.
+#include <map>
+#include <mutex>
+
 #include "vof_host_common.h"
 #include "vof2d_kernels.cuh"
 #include "vof2d_jacobi_tb.cuh"
@@ -64,6 +67,9 @@ struct VofCtx {
     // CUDA graphs of two consecutive steps, keyed by parity of the first istep and flags
     cudaGraphExec_t graph[2][4];
     long long graph_launches[2][4];
+    int graph_cur[2][4];       // (F_cur, p_cur) the graph was captured with: it hard-codes the ping-pong buffers
+    float* scratch;            // persistent device scratch of the display kernels (grown on demand)
+    size_t scratch_bytes;
     FctC fctx, fcty;           // constants of the FCT sweeps
     MomC mom;                  // constants of the momentum predictor
     JacTB jac;                 // constants of the temporally blocked Jacobi
@@ -113,8 +119,8 @@ static int resolve(const VofParams* in, VofParams* P, Grid* g, int* lo, int* hi,
         return fail(VOF_EINVAL, "slab rows [%d, %d] outside [1, %d]", P->slab_lo, P->slab_hi, P->nx);
     const bool full = (P->slab_lo == 1 && P->slab_hi == P->nx);
     if (!full) {
-        const int need = P->n_jacobi + 3;
-        if (P->halo < need) return fail(VOF_EINVAL, "slab halo %d < n_jacobi + 3 = %d", P->halo, need);
+        const int need = P->n_jacobi + 5;   // dependency radius of one step along i
+        if (P->halo < need) return fail(VOF_EINVAL, "slab halo %d < n_jacobi + 5 = %d", P->halo, need);
         if (P->slab_hi - P->slab_lo + 1 < P->halo)
             return fail(VOF_EINVAL, "slab of %d rows is thinner than its halo %d", P->slab_hi - P->slab_lo + 1, P->halo);
     }
@@ -133,6 +139,35 @@ extern "C" size_t vof2d_arena_bytes(const VofParams* p) {
     size_t xy = ((size_t)(P.nx + 3 + P.ny + 3) * sizeof(float) + 255) / 256 * 256;
     return field_stride_bytes(g.nrows, g.pitch) * BUF_COUNT + xy + 256;
 }
+
+// Proof that the reciprocal division by `d` is exact: every fp32 numerator against __fdiv_rn (4.8 ms per divisor).
+// The verdict depends on the divisor (and the device executing it) only, so it is cached: the 16 slab contexts of a
+// streamer, or repeated solver creation in a test session, prove each constant once.
+static int const_div_exact(VofCtx* c, const ConstDiv& d, bool* ok) {
+    static std::mutex mu;
+    static std::map<std::pair<int, unsigned int>, bool> verdicts;
+    unsigned int bits;
+    memcpy(&bits, &d.b, sizeof(bits));
+    const std::pair<int, unsigned int> key(c->device, bits);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = verdicts.find(key);
+        if (it != verdicts.end()) { *ok = it->second; return VOF_OK; }
+    }
+    unsigned long long* bad = &c->diag->courant_count;
+    unsigned long long h = 1;
+    CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
+    k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(d, bad);
+    CU(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
+    *ok = (h == 0);
+    std::lock_guard<std::mutex> lock(mu);
+    verdicts[key] = *ok;
+    return VOF_OK;
+}
+
+static int create_finish(VofCtx* c, void* arena, size_t arena_bytes, const std::vector<float>& x, const std::vector<float>& y);
 
 static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, VofCtx** out) {
     if (!out) return fail(VOF_EINVAL, "null out pointer");
@@ -225,20 +260,29 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     c->in_a = std::max(0, 1 - g.gi0);
     c->in_b = std::min(g.nrows - 1, P.nx - g.gi0);
 
+    // everything below can fail half-way: one cleanup path (vof2d_destroy copes with a partially built context)
+    rc = create_finish(c, arena, arena_bytes, x, y);
+    if (rc != VOF_OK) { vof2d_destroy(c); return rc; }
+    *out = c;
+    return VOF_OK;
+}
+
+static int create_finish(VofCtx* c, void* arena, size_t arena_bytes, const std::vector<float>& x, const std::vector<float>& y) {
+    const VofParams& P = c->P;
+    const Grid& g = c->g;
     const size_t need = vof2d_arena_bytes(&P);
     c->field_bytes = field_stride_bytes(g.nrows, g.pitch);
     if (arena) {
-        if (((uintptr_t)arena & 255) != 0) { delete c; return fail(VOF_EINVAL, "arena must be 256-byte aligned"); }
-        if (arena_bytes < need) { delete c; return fail(VOF_EINVAL, "arena too small: %zu < %zu", arena_bytes, need); }
+        if (((uintptr_t)arena & 255) != 0) return fail(VOF_EINVAL, "arena must be 256-byte aligned");
+        if (arena_bytes < need) return fail(VOF_EINVAL, "arena too small: %zu < %zu", arena_bytes, need);
         c->arena = (char*)arena; c->own_arena = false;
     } else {
-        e = cudaMalloc((void**)&c->arena, need);
-        if (e != cudaSuccess) { delete c; return fail(VOF_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", need, cudaGetErrorString(e)); }
+        cudaError_t e = cudaMalloc((void**)&c->arena, need);
+        if (e != cudaSuccess) { c->arena = nullptr; return fail(VOF_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", need, cudaGetErrorString(e)); }
         c->own_arena = true;
     }
     c->arena_bytes = need;
-    e = cudaMemset(c->arena, 0, need);   // the reference's fields start at zero (2dvof.py:53-89)
-    if (e != cudaSuccess) { if (c->own_arena) cudaFree(c->arena); delete c; return fail((int)e, "cudaMemset failed: %s", cudaGetErrorString(e)); }
+    CU(cudaMemset(c->arena, 0, need));   // the reference's fields start at zero (2dvof.py:53-89)
     for (int b = 0; b < BUF_COUNT; ++b) c->buf[b] = (float*)(c->arena + c->field_bytes * b) + kColOff;
     c->xs = (float*)(c->arena + c->field_bytes * BUF_COUNT);
     c->ys = c->xs + (P.nx + 3);
@@ -247,32 +291,17 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     CU(cudaMemcpy(c->ys, y.data(), y.size() * sizeof(float), cudaMemcpyHostToDevice));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
-    {   // prove the reciprocal division exact for this diagonal: every fp32 numerator against __fdiv_rn
-        unsigned long long* bad = &c->diag->courant_count;
-        CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
-        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->jac.dv[0], bad);
-        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->jac.dv[1], bad);
-        unsigned long long h = 1;
-        CU(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
-        c->jac.fast_div_ok = (h == 0);
-        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->fctx.d_dxdy, bad);
-        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->fctx.d_dy, bad);
-        CU(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
-        c->fctx.fast_div_ok = c->fcty.fast_div_ok = (h == 0);
-        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->mom.d_dx, bad);
-        k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(c->mom.d_dy, bad);
-        CU(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
-        c->mom.fast_div_ok = (h == 0);
+    {   // prove the reciprocal divisions exact for this grid's constants (falls back to IEEE division otherwise)
+        bool a = false, b = false;
+        TRY(const_div_exact(c, c->jac.dv[0], &a)); TRY(const_div_exact(c, c->jac.dv[1], &b));
+        c->jac.fast_div_ok = a && b;
+        TRY(const_div_exact(c, c->fctx.d_dxdy, &a)); TRY(const_div_exact(c, c->fctx.d_dy, &b));
+        c->fctx.fast_div_ok = c->fcty.fast_div_ok = a && b;
+        TRY(const_div_exact(c, c->mom.d_dx, &a)); TRY(const_div_exact(c, c->mom.d_dy, &b));
+        c->mom.fast_div_ok = a && b;
     }
     c->ev_pool = new std::vector<cudaEvent_t>();
     c->spans = new std::vector<ProfSpan>();
-    *out = c;
     return VOF_OK;
 }
 
@@ -285,13 +314,14 @@ extern "C" int vof2d_create_in(const VofParams* p, void* arena, size_t arena_byt
 extern "C" int vof2d_destroy(VofCtx* c) {
     if (!c) return VOF_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 4; ++b)
             if (c->graph[a][b]) cudaGraphExecDestroy(c->graph[a][b]);
     for (int sd = 0; sd < 2; ++sd) if (c->peer_arena[sd] && c->peer_ipc[sd]) cudaIpcCloseMemHandle(c->peer_arena[sd]);
     if (c->spans) { for (auto& sp : *c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); } delete c->spans; }
     if (c->ev_pool) { for (auto e : *c->ev_pool) cudaEventDestroy(e); delete c->ev_pool; }
+    if (c->scratch) cudaFree(c->scratch);
     if (c->own_arena && c->arena) cudaFree(c->arena);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);   // a caller-provided stream is left alone
     delete c;
@@ -696,6 +726,18 @@ extern "C" int vof2d_post_process_f(VofCtx* c) { CHECK_CTX(c); return run_post(c
 // ------------------------------------------------------------------------------------
 // display kernels, 2dvof.py:458-492 (+ rgb_buf.to_numpy(), 535): monitoring output, full-domain contexts only
 // ------------------------------------------------------------------------------------
+static int display_scratch(VofCtx* c, size_t bytes, float** out) {
+    if (c->scratch_bytes < bytes) {
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->scratch) cudaFree(c->scratch);
+        c->scratch = nullptr; c->scratch_bytes = 0;
+        if (cudaMalloc((void**)&c->scratch, bytes) != cudaSuccess) return fail(VOF_ENOMEM, "cudaMalloc(%zu bytes) for the display buffer failed", bytes);
+        c->scratch_bytes = bytes;
+    }
+    *out = c->scratch;
+    return VOF_OK;
+}
+
 static int display_dev(VofCtx* c, int view, float* rgb) {
     if (c->g.gi0 != 0 || c->g.nrows != c->g.nx + 2) return fail(VOF_ESTATE, "display kernels need a full-domain context");
     ++c->launches;
@@ -722,14 +764,13 @@ extern "C" int vof2d_display_field(VofCtx* c, int view, float* rgb_host) {
     CU(cudaSetDevice(c->device));
     const size_t bytes = (size_t)4 * c->g.nx * c->g.ny * sizeof(float);
     float* d = nullptr;
-    if (cudaMalloc((void**)&d, bytes) != cudaSuccess) return fail(VOF_ENOMEM, "cudaMalloc(%zu bytes) for rgb_buf failed", bytes);
+    TRY(display_scratch(c, bytes, &d));          // persistent: no cudaMalloc / cudaFree (device-wide syncs) per frame
     int rc = display_dev(c, view, d);
     if (rc == VOF_OK) {
         cudaError_t e = cudaMemcpyAsync(rgb_host, d, bytes, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = fail((int)e, "rgb_buf copy failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(d);
     return rc;
 }
 extern "C" int vof2d_interp_velocity(VofCtx* c, float* V_host) {
@@ -738,8 +779,9 @@ extern "C" int vof2d_interp_velocity(VofCtx* c, float* V_host) {
     if (c->g.gi0 != 0 || c->g.nrows != c->g.nx + 2) return fail(VOF_ESTATE, "display kernels need a full-domain context");
     CU(cudaSetDevice(c->device));
     const size_t bytes = (size_t)2 * (c->g.nx + 2) * (c->g.ny + 2) * sizeof(float);
-    float2* d = nullptr;
-    if (cudaMalloc((void**)&d, bytes) != cudaSuccess) return fail(VOF_ENOMEM, "cudaMalloc(%zu bytes) for V failed", bytes);
+    float* df = nullptr;
+    TRY(display_scratch(c, bytes, &df));
+    float2* d = (float2*)df;
     ++c->launches;
     k_interp_velocity<<<dim3(cdiv(c->g.ny + 2, 256), c->g.nx + 2), 256, 0, c->stream>>>(c->g, c->buf[BUF_U], c->buf[BUF_V], d);
     int rc = launch_ok("k_interp_velocity");
@@ -748,7 +790,6 @@ extern "C" int vof2d_interp_velocity(VofCtx* c, float* V_host) {
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = fail((int)e, "V copy failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(d);
     return rc;
 }
 
@@ -805,6 +846,13 @@ extern "C" int vof2d_run(VofCtx* c, int istep0, int nsteps, unsigned flags) {
     if (left >= 4 && !c->profiling) {
         // capture two consecutive steps (the FCT sweep order alternates with istep parity; after two
         // steps every ping-pong buffer is back where it started, so the graph can be replayed)
+        // the captured launches hard-code the ping-pong buffers of capture time: a graph taken with another
+        // (F_cur, p_cur) -- e.g. after a single vof2d_fct_x_sweep or one Jacobi sweep between two runs -- is stale
+        const int cur = c->F_cur | (c->p_cur << 1);
+        if (c->graph[par][fk] && c->graph_cur[par][fk] != cur) {
+            cudaGraphExecDestroy(c->graph[par][fk]);
+            c->graph[par][fk] = nullptr;
+        }
         if (!c->graph[par][fk]) {
             const int F0 = c->F_cur, p0 = c->p_cur;
             const long long l0 = c->launches;
@@ -821,6 +869,7 @@ extern "C" int vof2d_run(VofCtx* c, int istep0, int nsteps, unsigned flags) {
             e = cudaGraphInstantiate(&c->graph[par][fk], gr, 0);
             cudaGraphDestroy(gr);
             if (e != cudaSuccess) { c->graph[par][fk] = nullptr; return fail((int)e, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+            c->graph_cur[par][fk] = cur;
         }
         while (left >= 2) {
             CU(cudaGraphLaunch(c->graph[par][fk], c->stream));
@@ -950,16 +999,22 @@ extern "C" int vof2d_diagnostics(VofCtx* c, double* mass, float* max_cfl, float*
 //   wait   done(e) from both neighbours, push my boundary rows of u, v, p, F into their halo rows,
 //   signal data(e), wait data(e) from both neighbours.
 // ------------------------------------------------------------------------------------
-struct P2PFlags { unsigned int done_from[2]; unsigned int data_from[2]; unsigned int timeout; unsigned int pad[3]; };
+// `cur_from`: which ping-pong buffers (F_cur | p_cur << 1, tagged with the epoch) the neighbour on that side holds its
+// live F and p in.  The push addresses the neighbour's buffers by MY F_cur / p_cur, i.e. it assumes the ranks run in
+// lockstep; the tag turns a violation (a rank that called an extra sweep) into an error instead of silent garbage.
+struct P2PFlags { unsigned int done_from[2]; unsigned int data_from[2]; unsigned int timeout; unsigned int mismatch; unsigned int cur_from[2]; };
 
-__global__ void k_p2p_signal(unsigned int* lo_flag, unsigned int* hi_flag, unsigned int epoch) {
+__global__ void k_p2p_signal(unsigned int* lo_flag, unsigned int* hi_flag, unsigned int epoch, unsigned int* lo_cur, unsigned int* hi_cur, unsigned int cur) {
+    if (lo_cur) *reinterpret_cast<volatile unsigned int*>(lo_cur) = (epoch << 2) | cur;
+    if (hi_cur) *reinterpret_cast<volatile unsigned int*>(hi_cur) = (epoch << 2) | cur;
     __threadfence_system();
     if (lo_flag) *reinterpret_cast<volatile unsigned int*>(lo_flag) = epoch;
     if (hi_flag) *reinterpret_cast<volatile unsigned int*>(hi_flag) = epoch;
     __threadfence_system();
 }
 
-__global__ void k_p2p_wait(const unsigned int* a, const unsigned int* b, unsigned int epoch, unsigned int* timeout_flag) {
+__global__ void k_p2p_wait(const unsigned int* a, const unsigned int* b, unsigned int epoch, unsigned int* timeout_flag,
+                           const unsigned int* cur_a, const unsigned int* cur_b, unsigned int cur, unsigned int* mismatch_flag) {
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (int q = 0; q < 2; ++q) {
@@ -973,6 +1028,12 @@ __global__ void k_p2p_wait(const unsigned int* a, const unsigned int* b, unsigne
         }
     }
     __threadfence_system();
+    for (int q = 0; q < 2; ++q) {
+        const volatile unsigned int* f = q == 0 ? cur_a : cur_b;
+        if (!f) continue;
+        const unsigned int v = *f;
+        if ((v >> 2) == epoch && (v & 3u) != cur) *mismatch_flag = epoch;     // the neighbour's live buffers are not mine
+    }
 }
 
 // copy `count4` float4 per field from my send rows to the peer's halo rows; blockIdx.y = field * 2 + side
@@ -1123,8 +1184,9 @@ extern "C" int vof2d_p2p_connect(VofCtx* c, int side, const void* handle64, void
     CU(cudaFuncGetAttributes(&fa, k_p2p_signal));
     CU(cudaFuncGetAttributes(&fa, k_p2p_wait));
     CU(cudaFuncGetAttributes(&fa, k_p2p_push));
-    k_p2p_signal<<<1, 1, 0, c->stream>>>(nullptr, nullptr, 0u);
-    k_p2p_wait<<<1, 1, 0, c->stream>>>(nullptr, nullptr, 0u, &flags_of(c->arena, c->arena_bytes)->timeout);
+    k_p2p_signal<<<1, 1, 0, c->stream>>>(nullptr, nullptr, 0u, nullptr, nullptr, 0u);
+    k_p2p_wait<<<1, 1, 0, c->stream>>>(nullptr, nullptr, 0u, &flags_of(c->arena, c->arena_bytes)->timeout, nullptr, nullptr, 0u,
+                                       &flags_of(c->arena, c->arena_bytes)->mismatch);
     P2PPush none; memset(&none, 0, sizeof(none));
     k_p2p_push<<<dim3(1, 8), 256, 0, c->stream>>>(none, 0);
     CU(cudaStreamSynchronize(c->stream));
@@ -1145,8 +1207,11 @@ extern "C" int vof2d_halo_exchange_p2p(VofCtx* c) {
     P2PFlags* plo = nlo ? flags_of(c->peer_arena[0], arena_bytes_for_rows(c, c->peer_nrows[0])) : nullptr;
     P2PFlags* phi = nhi ? flags_of(c->peer_arena[1], arena_bytes_for_rows(c, c->peer_nrows[1])) : nullptr;
     // I am the lower neighbour's upper side (index 1) and the upper neighbour's lower side (index 0)
-    k_p2p_signal<<<1, 1, 0, c->stream>>>(plo ? &plo->done_from[1] : nullptr, phi ? &phi->done_from[0] : nullptr, e);
-    k_p2p_wait<<<1, 1, 0, c->stream>>>(nlo ? &mine->done_from[0] : nullptr, nhi ? &mine->done_from[1] : nullptr, e, &mine->timeout);
+    const unsigned int cur = (unsigned int)(c->F_cur | (c->p_cur << 1));
+    k_p2p_signal<<<1, 1, 0, c->stream>>>(plo ? &plo->done_from[1] : nullptr, phi ? &phi->done_from[0] : nullptr, e,
+                                         plo ? &plo->cur_from[1] : nullptr, phi ? &phi->cur_from[0] : nullptr, cur);
+    k_p2p_wait<<<1, 1, 0, c->stream>>>(nlo ? &mine->done_from[0] : nullptr, nhi ? &mine->done_from[1] : nullptr, e, &mine->timeout,
+                                       nlo ? &mine->cur_from[0] : nullptr, nhi ? &mine->cur_from[1] : nullptr, cur, &mine->mismatch);
     P2PPush a;
     memset(&a, 0, sizeof(a));
     const int H = c->H, n = c->g.nrows, P = c->g.pitch;
@@ -1166,8 +1231,9 @@ extern "C" int vof2d_halo_exchange_p2p(VofCtx* c) {
     }
     const long long count4 = (long long)H * P / 4;     // pitch is a multiple of 32 floats
     k_p2p_push<<<dim3(32, 8), 256, 0, c->stream>>>(a, count4);
-    k_p2p_signal<<<1, 1, 0, c->stream>>>(plo ? &plo->data_from[1] : nullptr, phi ? &phi->data_from[0] : nullptr, e);
-    k_p2p_wait<<<1, 1, 0, c->stream>>>(nlo ? &mine->data_from[0] : nullptr, nhi ? &mine->data_from[1] : nullptr, e, &mine->timeout);
+    k_p2p_signal<<<1, 1, 0, c->stream>>>(plo ? &plo->data_from[1] : nullptr, phi ? &phi->data_from[0] : nullptr, e, nullptr, nullptr, 0u);
+    k_p2p_wait<<<1, 1, 0, c->stream>>>(nlo ? &mine->data_from[0] : nullptr, nhi ? &mine->data_from[1] : nullptr, e, &mine->timeout,
+                                       nullptr, nullptr, 0u, &mine->mismatch);
     return launch_ok("p2p halo exchange");
 }
 
@@ -1178,6 +1244,19 @@ extern "C" int vof2d_p2p_status(VofCtx* c, int* timed_out_epoch) {
     CU(cudaMemcpyAsync(&t, &flags_of(c->arena, c->arena_bytes)->timeout, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (timed_out_epoch) *timed_out_epoch = (int)t;
+    return VOF_OK;
+}
+
+// Error (VOF_ESTATE) if any halo exchange so far gave up waiting for a neighbour (20 s watchdog) or found the
+// neighbour's ping-pong buffers out of step with this rank's.  Synchronises the stream: call it every N steps.
+extern "C" int vof2d_p2p_check(VofCtx* c) {
+    CHECK_CTX(c);
+    CU(cudaSetDevice(c->device));
+    unsigned int t[2] = {0, 0};
+    CU(cudaMemcpyAsync(t, &flags_of(c->arena, c->arena_bytes)->timeout, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (t[0]) return fail(VOF_ESTATE, "halo exchange %u timed out waiting for a neighbour (20 s); the halo rows since then are stale", t[0]);
+    if (t[1]) return fail(VOF_ESTATE, "halo exchange %u: a neighbour holds F / p in the other ping-pong buffer (ranks are not in lockstep)", t[1]);
     return VOF_OK;
 }
 
@@ -1216,7 +1295,7 @@ extern "C" int vof2d_streamer_create(const VofParams* p, int n_slabs, VofStreame
     *out = nullptr;
     if (!p) return fail(VOF_EINVAL, "null params");
     if (p->slab_lo != 0 || p->slab_hi != 0) return fail(VOF_EINVAL, "the streamer takes full-domain params (slab_lo = slab_hi = 0)");
-    const int H = std::max(p->halo, p->n_jacobi + 3);
+    const int H = std::max(p->halo, p->n_jacobi + 5);
     if (n_slabs < 1 || (n_slabs > 1 && p->nx / n_slabs < H))
         return fail(VOF_EINVAL, "%d slabs of a %d-row domain are thinner than the halo %d", n_slabs, p->nx, H);
     VofStreamer* st = new VofStreamer;

@@ -53,8 +53,8 @@ static int resolve3(const VofParams* in, VofParams* P, Grid3* g) {
     if (P->slab_lo < 1 || P->slab_hi > P->nx || P->slab_lo > P->slab_hi)
         return fail(VOF_EINVAL, "slab planes [%d, %d] outside [1, %d]", P->slab_lo, P->slab_hi, P->nx);
     if (!(P->slab_lo == 1 && P->slab_hi == P->nx)) {
-        const int need = P->n_jacobi + 3;
-        if (P->halo < need) return fail(VOF_EINVAL, "slab halo %d < n_jacobi + 3 = %d", P->halo, need);
+        const int need = P->n_jacobi + 4;   // no curvature in 3-D: F_new(i) <- u_new(i+3) <- rhs(i+2+n) <- u*(i+3+n) <- u(i+4+n)
+        if (P->halo < need) return fail(VOF_EINVAL, "slab halo %d < n_jacobi + 4 = %d", P->halo, need);
         if (P->slab_hi - P->slab_lo + 1 < P->halo) return fail(VOF_EINVAL, "slab is thinner than its halo");
     }
     g->nx = P->nx; g->ny = P->ny; g->nz = P->nz;

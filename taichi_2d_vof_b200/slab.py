@@ -2,8 +2,9 @@
 single-address-space).
 
 Design: communication-avoiding deep halos.  The whole timestep has a dependency radius of
-``n_jacobi + 3`` rows along i (kappa 2, advect +1, ten Jacobi sweeps +10 ... the x-FCT needs u at
-i+3 -- see DESIGN.md), so each rank keeps H >= n_jacobi + 3 ghost rows per side, recomputes
+``n_jacobi + 5`` rows along i (the x-FCT reads u at i+3, u needs p after n sweeps, whose rhs reaches
+n-1 rows further and reads u* one row up, whose CSF term reads kappa, i.e. F three rows away -- see
+DESIGN.md section 5), so each rank keeps H >= n_jacobi + 5 ghost rows per side, recomputes
 the few halo rows redundantly, and exchanges u, v, p, F ONCE per step (4 fields x H contiguous
 pitched rows per neighbour) instead of once per sweep.  Physical-wall logic applies only on the
 first / last rank; interior ranks see their neighbours' rows as ordinary cells.
@@ -33,8 +34,9 @@ def partition(nx: int, nranks: int) -> List[Tuple[int, int]]:
 
 
 def required_halo(n_jacobi: int) -> int:
-    """Dependency radius of one step along i (matches VOF_SLAB_MIN_HALO for n_jacobi = 10)."""
-    return n_jacobi + 3
+    """Dependency radius of one step along i (matches VOF_SLAB_MIN_HALO for n_jacobi = 10):
+    F_new(i) <- u_new(i+3) <- p_n(i+3) <- rhs(i+3+n-1) <- u*(i+3+n) <- kappa(i+3+n) <- F(i+5+n)."""
+    return n_jacobi + 5
 
 
 def halo_row_blocks(nrows: int, halo: int):

@@ -311,6 +311,10 @@ class VofSolver2D:
         check(self._L.vof2d_p2p_status(self._h, C.byref(t)))
         return t.value
 
+    def p2p_check(self):
+        """Raises VofError if a halo exchange timed out or the neighbours are out of lockstep (synchronises)."""
+        check(self._L.vof2d_p2p_check(self._h))
+
     def halo_push(self, name, side, peer_dst):
         check(self._L.vof2d_halo_push(self._h, _lib.FIELD_IDS[name], side, C.c_void_p(peer_dst)))
 

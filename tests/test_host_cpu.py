@@ -68,7 +68,7 @@ def test_argument_errors(built_lib):
     assert built_lib.vof2d_create(C.byref(p), C.byref(h)) == -1
     assert b"nx, ny" in built_lib.vof_last_error()
     built_lib.vof_default_params(C.byref(p))
-    p.slab_lo, p.slab_hi, p.halo = 1, 100, 5          # a slab needs halo >= n_jacobi + 3
+    p.slab_lo, p.slab_hi, p.halo = 1, 100, 5          # a slab needs halo >= n_jacobi + 5
     assert built_lib.vof2d_create(C.byref(p), C.byref(h)) == -1
     assert b"halo" in built_lib.vof_last_error()
     assert built_lib.vof2d_set_BC(None) == -1
@@ -92,7 +92,7 @@ def test_partition_and_halo_blocks():
     assert parts[0] == (1, 4096) and parts[-1] == (28673, 32768)
     parts = partition(10, 3)
     assert parts == [(1, 4), (5, 7), (8, 10)]
-    assert required_halo(10) == 13
+    assert required_halo(10) == 15
     assert halo_row_blocks(100, 16) == ((16, 32), (0, 16), (68, 84), (84, 100))
     with pytest.raises(ValueError):
         partition(2, 3)

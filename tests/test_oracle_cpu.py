@@ -241,3 +241,53 @@ def test_c_oracle_reproduces_golden_3d(path):
         for k in ("u", "v", "w", "p", "F"):
             assert np.array_equal(getattr(o, k), g[f"{k}_{ck}"]), f"{k} after {ck} steps"
         assert abs(o.mass() - float(g[f"mass_{ck}"])) <= 1e-9 * float(g[f"mass_{ck}"])
+
+
+# ----------------------------------------------------------------------------------------------
+# dependency radius of one step along i: what the slab halo depth must cover
+# ----------------------------------------------------------------------------------------------
+def _band_after_step(n_jacobi, R, seed, three_d=False):
+    """Two fp64 states that agree only within R rows of the band [a, b]; returns whether the band agrees after one step."""
+    if three_d:
+        from oracle.vof3d_oracle import Vof3DOracle, Vof3DParams
+        P = Vof3DParams(nx=72, ny=5, nz=6, Lx=0.036, Ly=0.0025, Lz=0.003, n_jacobi=n_jacobi)
+        mk, vels = (lambda: Vof3DOracle(P, real=np.float64)), ("u", "v", "w")
+    else:
+        P = Vof2DParams(nx=72, ny=20, Lx=0.036, Ly=0.01, n_jacobi=n_jacobi)
+        mk, vels = (lambda: Vof2DOracle(P, real=np.float64)), ("u", "v")
+    a, b = 34, 38
+    out = []
+    for variant in (0, 1):
+        o = mk()
+        rng, far = np.random.default_rng(seed), np.random.default_rng(seed + 1000 + variant)
+        vel = 0.2 * P.dx / P.dt                                   # CFL ~ 0.2: upwind switches and the limiter are live
+        for k in ("F",) + vels + ("p",):
+            arr = getattr(o, k)
+            scale = 1.0 if k in ("F", "p") else vel
+            arr[...] = (rng.random(arr.shape) * (1 if k == "F" else 2) - (0 if k == "F" else 1)) * scale
+            other = (far.random(arr.shape) * (1 if k == "F" else 2) - (0 if k == "F" else 1)) * scale
+            arr[: a - R] = other[: a - R]
+            arr[b + R + 1:] = other[b + R + 1:]
+        o.step()
+        out.append({k: getattr(o, k)[a:b + 1].copy() for k in ("F",) + vels + ("p",)})
+    return all(np.array_equal(out[0][k], out[1][k]) for k in out[0])
+
+
+@pytest.mark.parametrize("n_jacobi", [10, 4, 1])
+def test_step_dependency_radius_2d(n_jacobi):
+    """One 2-D step reads n_jacobi + 5 rows either side (x-FCT <- u(i+3) <- p after n sweeps <- rhs <- u* <- kappa <- F):
+    rows further away cannot influence a row, rows n_jacobi + 5 away do."""
+    from taichi_2d_vof_b200.slab import required_halo
+    R = required_halo(n_jacobi)
+    assert R == n_jacobi + 5
+    for seed in range(4):
+        assert _band_after_step(n_jacobi, R, seed)
+    if n_jacobi <= 4:     # tightness (after 9 sweeps the farthest influence, ~4^-9 of an ulp-level term, drops out of fp64)
+        assert not all(_band_after_step(n_jacobi, R - 1, seed) for seed in range(4)), "n_jacobi + 4 rows would do?"
+
+
+def test_step_dependency_radius_3d():
+    """3-D (no curvature): n_jacobi + 4 planes."""
+    for seed in range(2):
+        assert _band_after_step(10, 14, seed, three_d=True)
+        assert _band_after_step(3, 7, seed, three_d=True)

@@ -128,7 +128,7 @@ def test_streamed_step_host(built_lib, nx, ny, n_slabs, inplace):
     P = Vof2DParams(nx=nx, ny=ny, Lx=0.0005 * nx, Ly=0.0005 * ny)
     o = Vof2DOracle(P); o.set_init_F(3)
     st = VofStreamer2D(_params(P), n_slabs=n_slabs)
-    assert st.n_slabs == n_slabs and (n_slabs == 1 or st.halo >= P.n_jacobi + 3)
+    assert st.n_slabs == n_slabs and (n_slabs == 1 or st.halo >= P.n_jacobi + 5)
     a = [getattr(o, k).copy() for k in ("u", "v", "p", "F")]
     b = [np.empty_like(x) for x in a]
     for step in range(6):
