@@ -148,8 +148,11 @@ def test_slabs_with_minimal_halo_on_a_live_state(built_lib, n_jacobi):
     for name, a in (("u", u), ("v", v), ("p", p), ("F", F)):
         getattr(full, name).from_numpy(a)
         getattr(o, name)[...] = a
-        for r, s in enumerate(grp.solvers):
-            getattr(s, name).from_numpy(a[s.gi0:s.gi0 + s.nrows])
+        for s in grp.solvers:                       # local row l holds global row gi0 + l (rows outside the domain: unused)
+            loc = np.zeros((s.nrows, ny + 2), np.float32)
+            g0, g1 = max(s.gi0, 0), min(s.gi0 + s.nrows, nx + 2)
+            loc[g0 - s.gi0:g1 - s.gi0] = a[g0:g1]
+            getattr(s, name).from_numpy(loc)
     for step in range(1, 4):
         full.step(); grp.step(); o.step()
         for k in ("F", "u", "v", "p"):
@@ -184,14 +187,15 @@ def test_graph_replay_after_an_odd_number_of_buffer_flips(built_lib):
     P = Vof2DParams(nx=96, ny=80, Lx=0.048, Ly=0.04)
     o = Vof2DOracle(P); o.set_init_F(3)
     s = VofSolver2D(reference_params(nx=96, ny=80, Lx=0.048, Ly=0.04)); s.set_init_F(3)
-    o.run(6); s.run(6)
+    # materialised rho / nu: the single-kernel entries read the arrays, as the reference's kernels do
+    o.run(6); s.run(6, materialize_props=True)
     o.fct_x_sweep(); s.fct_x_sweep()              # F_cur flips once
     o.solve_p_jacobi(); s.solve_p_jacobi()        # p_cur flips once
-    o.run(6); s.run(6)
+    o.run(6); s.run(6, materialize_props=True)
     for k in ("F", "u", "v", "p"):
         _same(getattr(s, k).to_numpy(), getattr(o, k), f"graph replay after flips, field {k}")
     o.fct_y_sweep(); s.fct_y_sweep()
-    o.run(4); s.run(4)
+    o.run(4); s.run(4, materialize_props=True)
     for k in ("F", "u", "v", "p"):
         _same(getattr(s, k).to_numpy(), getattr(o, k), f"second replay after a flip, field {k}")
 
