@@ -140,6 +140,13 @@ int vof2d_field_ptr(VofCtx* c, int field, float** dev, int64_t* pitch_elems, int
 int vof2d_field_get(VofCtx* c, int field, float* host_dst);        /* logical rows of this ctx */
 int vof2d_field_set(VofCtx* c, int field, const float* host_src);
 int vof2d_field_fill(VofCtx* c, int field, float value);
+/* Non-stalling read for the -s output path (F.to_numpy() at 2dvof.py:565 / 3dvof.py:627 blocks the reference's loop):
+ * the field is snapshotted on the compute stream and copied to host_dst (pinned: vof_pinned_alloc) on a side stream
+ * while the time loop continues; host_dst is valid after *_field_get_wait.  One read in flight per context. */
+int vof2d_field_get_async(VofCtx* c, int field, float* host_dst);
+int vof2d_field_get_wait(VofCtx* c);
+int vof_pinned_alloc(size_t bytes, void** out);
+int vof_pinned_free(void* ptr);
 
 /* ---- diagnostics (new; the reference only prints on Courant violation, 2dvof.py:274-280) ----
  * mass = sum F over owned interior cells (fp64), max_cfl = max(|u|dt/dx, |v|dt/dy),
@@ -232,12 +239,20 @@ int vof3d_step(Vof3Ctx* c, int istep, unsigned flags);     /* 3dvof.py:606-623  
 int vof3d_run(Vof3Ctx* c, int istep0, int nsteps, unsigned flags);
 int vof3d_field_ptr(Vof3Ctx* c, int field, float** dev, int64_t* pitch_k, int64_t* pitch_j, int64_t* planes);
 int vof3d_field_get(Vof3Ctx* c, int field, float* host_dst);   /* F.to_numpy(), 3dvof.py:627         */
+int vof3d_field_get_async(Vof3Ctx* c, int field, float* host_dst);   /* see vof2d_field_get_async */
+int vof3d_field_get_wait(Vof3Ctx* c);
 int vof3d_field_set(Vof3Ctx* c, int field, const float* host_src);
 int vof3d_set_option(Vof3Ctx* c, int option, int value);      /* VOF_OPT_ADAPTIVE: 1 (default) second-generation kernels, 0 first */
 int vof3d_diagnostics(Vof3Ctx* c, double* mass, float* max_cfl, int64_t* courant_count);
 int64_t vof3d_launch_count(const Vof3Ctx* c);
 int vof3d_halo_ptr(Vof3Ctx* c, int field, int side, int send, float** dev, int64_t* count);
 int vof3d_halo_push(Vof3Ctx* c, int field, int side, float* peer_halo_dst);
+/* NVLink peer-store exchange of the halo planes of u, v, w, p, F (same protocol as vof2d_*_p2p, one kernel per step) */
+int vof3d_p2p_export(Vof3Ctx* c, void* handle64, int64_t* nrows, int64_t* arena_bytes);
+int vof3d_p2p_connect(Vof3Ctx* c, int side, const void* handle64, void* same_process_arena, int64_t peer_nrows);
+int vof3d_p2p_arena(Vof3Ctx* c, void** arena);
+int vof3d_halo_exchange_p2p(Vof3Ctx* c);
+int vof3d_p2p_check(Vof3Ctx* c);
 
 #ifdef __cplusplus
 }

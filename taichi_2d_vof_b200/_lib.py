@@ -104,6 +104,10 @@ SIGNATURES = {
     "vof2d_field_get": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
     "vof2d_field_set": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
     "vof2d_field_fill": (C.c_int, [_ctx, C.c_int, C.c_float]),
+    "vof2d_field_get_async": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
+    "vof2d_field_get_wait": (C.c_int, [_ctx]),
+    "vof_pinned_alloc": (C.c_int, [C.c_size_t, _P(C.c_void_p)]),
+    "vof_pinned_free": (C.c_int, [C.c_void_p]),
     "vof2d_diagnostics": (C.c_int, [_ctx, _P(C.c_double), _P(C.c_float), _P(C.c_float), _P(C.c_int64)]),
     "vof2d_launch_count": (C.c_int64, [_ctx]),
     "vof2d_profile": (C.c_int, [_ctx, C.c_int]),
@@ -141,11 +145,18 @@ SIGNATURES = {
     "vof3d_field_ptr": (C.c_int, [_ctx, C.c_int, _P(C.c_void_p), _P(C.c_int64), _P(C.c_int64), _P(C.c_int64)]),
     "vof3d_field_get": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
     "vof3d_field_set": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
+    "vof3d_field_get_async": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
+    "vof3d_field_get_wait": (C.c_int, [_ctx]),
     "vof3d_diagnostics": (C.c_int, [_ctx, _P(C.c_double), _P(C.c_float), _P(C.c_int64)]),
     "vof3d_launch_count": (C.c_int64, [_ctx]),
     "vof3d_set_option": (C.c_int, [_ctx, C.c_int, C.c_int]),
     "vof3d_halo_ptr": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _P(C.c_void_p), _P(C.c_int64)]),
     "vof3d_halo_push": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p]),
+    "vof3d_p2p_export": (C.c_int, [_ctx, C.c_void_p, _P(C.c_int64), _P(C.c_int64)]),
+    "vof3d_p2p_connect": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]),
+    "vof3d_p2p_arena": (C.c_int, [_ctx, _P(C.c_void_p)]),
+    "vof3d_halo_exchange_p2p": (C.c_int, [_ctx]),
+    "vof3d_p2p_check": (C.c_int, [_ctx]),
 }
 
 
@@ -164,6 +175,27 @@ def lib():
             fn.argtypes = args
         _LIB = L
     return _LIB
+
+
+def pinned_empty(shape, dtype="float32"):
+    """A page-locked NumPy array (cudaHostAlloc through the C ABI): the target of the non-stalling field reads."""
+    import numpy as np
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = C.c_void_p()
+    check(lib().vof_pinned_alloc(n, C.byref(ptr)))
+    buf = (C.c_char * n).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _PINNED[arr.__array_interface__["data"][0]] = ptr.value
+    return arr
+
+
+def pinned_free(arr):
+    ptr = _PINNED.pop(arr.__array_interface__["data"][0], None)
+    if ptr:
+        check(lib().vof_pinned_free(C.c_void_p(ptr)))
+
+
+_PINNED = {}
 
 
 def check(rc: int):

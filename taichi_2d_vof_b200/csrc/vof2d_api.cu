@@ -9,6 +9,7 @@
 #include "vof2d_fct.cuh"
 #include "vof2d_momentum.cuh"
 #include "vof2d_kappa.cuh"
+#include "vof_p2p.cuh"
 
 using namespace vof;
 
@@ -68,6 +69,7 @@ struct VofCtx {
     cudaGraphExec_t graph[2][4];
     long long graph_launches[2][4];
     int graph_cur[2][4];       // (F_cur, p_cur) the graph was captured with: it hard-codes the ping-pong buffers
+    vofhost::AsyncGet* aget;   // non-stalling field read for the output path (vof2d_field_get_async)
     float* scratch;            // persistent device scratch of the display kernels (grown on demand)
     size_t scratch_bytes;
     FctC fctx, fcty;           // constants of the FCT sweeps
@@ -83,10 +85,7 @@ struct VofCtx {
     int opt_fit_rounds;        // 1: item sizes of the queue kernels are fitted to whole rounds of the resident warps (measured: no gain; default 0)
     int opt_chunk_cap;         // > 0: upper bound on the rows one warp marches in the streaming kernels (load-balance experiments)
     int opt_adaptive;          // 1: interface-adaptive kernels (warp-uniform bulk rows short-cut, cp.async ring), 0: first generation
-    char* peer_arena[2];       // neighbour arenas mapped into this process (lower / upper), NVLink P2P
-    long long peer_nrows[2];
-    bool peer_ipc[2];
-    unsigned int p2p_epoch;
+    P2PEndpoint p2p;           // neighbour arenas mapped into this process (lower / upper), NVLink P2P
     int sm_count;
     // launch accounting + optional per-kernel-kind CUDA-event timing (vof2d_profile)
     long long launches;
@@ -318,10 +317,11 @@ extern "C" int vof2d_destroy(VofCtx* c) {
     for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 4; ++b)
             if (c->graph[a][b]) cudaGraphExecDestroy(c->graph[a][b]);
-    for (int sd = 0; sd < 2; ++sd) if (c->peer_arena[sd] && c->peer_ipc[sd]) cudaIpcCloseMemHandle(c->peer_arena[sd]);
+    p2p_close(c->p2p);
     if (c->spans) { for (auto& sp : *c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); } delete c->spans; }
     if (c->ev_pool) { for (auto e : *c->ev_pool) cudaEventDestroy(e); delete c->ev_pool; }
     if (c->scratch) cudaFree(c->scratch);
+    if (c->aget) { vofhost::async_get_free(*c->aget); delete c->aget; }
     if (c->own_arena && c->arena) cudaFree(c->arena);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);   // a caller-provided stream is left alone
     delete c;
@@ -921,6 +921,36 @@ extern "C" int vof2d_field_get(VofCtx* c, int field, float* host_dst) {
     return VOF_OK;
 }
 
+// Non-stalling read for the output path (-s, 2dvof.py:563-571): snapshot on the compute stream, D2H on a side stream.
+// `host_dst` (dense (rows, ny+2) fp32; pinned memory for a true overlap, see vof_pinned_alloc) is valid after
+// vof2d_field_get_wait.  One read in flight per context: a second call waits for the first one's copy.
+extern "C" int vof2d_field_get_async(VofCtx* c, int field, float* host_dst) {
+    CHECK_CTX(c);
+    float* d = field_dev(c, field);
+    if (!d || !host_dst) return fail(VOF_EINVAL, "bad field id %d or null destination", field);
+    CU(cudaSetDevice(c->device));
+    if (!c->aget) c->aget = new vofhost::AsyncGet();
+    return vofhost::async_get_begin(*c->aget, c->stream, d - kColOff, c->field_bytes, (size_t)c->g.pitch * sizeof(float),
+                                    (size_t)(c->g.ny + 2) * sizeof(float), (size_t)c->g.nrows, (size_t)kColOff * sizeof(float), host_dst);
+}
+extern "C" int vof2d_field_get_wait(VofCtx* c) {
+    CHECK_CTX(c);
+    if (!c->aget) return VOF_OK;
+    CU(cudaSetDevice(c->device));
+    return vofhost::async_get_wait(*c->aget);
+}
+extern "C" int vof_pinned_alloc(size_t bytes, void** out) {
+    if (!out) return fail(VOF_EINVAL, "null out pointer");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(VOF_ENOMEM, "cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    return VOF_OK;
+}
+extern "C" int vof_pinned_free(void* ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return VOF_OK;
+}
+
 static int field_set_async(VofCtx* c, int field, const float* host_src) {
     float* d = field_dev(c, field);
     if (!d || !host_src) return fail(VOF_EINVAL, "bad field id %d or null source", field);
@@ -992,60 +1022,11 @@ extern "C" int vof2d_diagnostics(VofCtx* c, double* mass, float* max_cfl, float*
 }
 
 // ------------------------------------------------------------------------------------
-// NVLink peer-to-peer halo exchange: kernels store straight into the neighbour's halo rows (peer-mapped
-// arena, CUDA IPC) and hand-shake through flags in the neighbour's memory -- no NCCL, no host synchronisation.
-// Per exchange (epoch e), all stream-ordered on the context's stream:
-//   signal done(e) to both neighbours ("my previous step no longer reads my halo rows")
-//   wait   done(e) from both neighbours, push my boundary rows of u, v, p, F into their halo rows,
-//   signal data(e), wait data(e) from both neighbours.
+// NVLink peer-to-peer halo exchange: see vof_p2p.cuh (one fused kernel per exchange).
 // ------------------------------------------------------------------------------------
 // `cur_from`: which ping-pong buffers (F_cur | p_cur << 1, tagged with the epoch) the neighbour on that side holds its
 // live F and p in.  The push addresses the neighbour's buffers by MY F_cur / p_cur, i.e. it assumes the ranks run in
 // lockstep; the tag turns a violation (a rank that called an extra sweep) into an error instead of silent garbage.
-struct P2PFlags { unsigned int done_from[2]; unsigned int data_from[2]; unsigned int timeout; unsigned int mismatch; unsigned int cur_from[2]; };
-
-__global__ void k_p2p_signal(unsigned int* lo_flag, unsigned int* hi_flag, unsigned int epoch, unsigned int* lo_cur, unsigned int* hi_cur, unsigned int cur) {
-    if (lo_cur) *reinterpret_cast<volatile unsigned int*>(lo_cur) = (epoch << 2) | cur;
-    if (hi_cur) *reinterpret_cast<volatile unsigned int*>(hi_cur) = (epoch << 2) | cur;
-    __threadfence_system();
-    if (lo_flag) *reinterpret_cast<volatile unsigned int*>(lo_flag) = epoch;
-    if (hi_flag) *reinterpret_cast<volatile unsigned int*>(hi_flag) = epoch;
-    __threadfence_system();
-}
-
-__global__ void k_p2p_wait(const unsigned int* a, const unsigned int* b, unsigned int epoch, unsigned int* timeout_flag,
-                           const unsigned int* cur_a, const unsigned int* cur_b, unsigned int cur, unsigned int* mismatch_flag) {
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (int q = 0; q < 2; ++q) {
-        const volatile unsigned int* f = q == 0 ? a : b;
-        if (!f) continue;
-        while ((int)(*f - epoch) < 0) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            if (t - t0 > 20000000000ull) { *timeout_flag = epoch; return; }   // 20 s: a neighbour died; do not hang the GPU
-            __nanosleep(200);
-        }
-    }
-    __threadfence_system();
-    for (int q = 0; q < 2; ++q) {
-        const volatile unsigned int* f = q == 0 ? cur_a : cur_b;
-        if (!f) continue;
-        const unsigned int v = *f;
-        if ((v >> 2) == epoch && (v & 3u) != cur) *mismatch_flag = epoch;     // the neighbour's live buffers are not mine
-    }
-}
-
-// copy `count4` float4 per field from my send rows to the peer's halo rows; blockIdx.y = field * 2 + side
-struct P2PPush { const float4* src[8]; float4* dst[8]; };
-__global__ void __launch_bounds__(256)
-k_p2p_push(P2PPush a, long long count4) {
-    const float4* __restrict__ src = a.src[blockIdx.y];
-    float4* __restrict__ dst = a.dst[blockIdx.y];
-    if (!src || !dst) return;
-    for (long long k = blockIdx.x * 256ll + threadIdx.x; k < count4; k += (long long)gridDim.x * 256) dst[k] = src[k];
-}
-
 // ------------------------------------------------------------------------------------
 // slabs: halo rows are contiguous (rows * pitch floats, pad columns included)
 // ------------------------------------------------------------------------------------
@@ -1140,8 +1121,6 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
 // ------------------------------------------------------------------------------------
 // P2P halo exchange API
 // ------------------------------------------------------------------------------------
-static P2PFlags* flags_of(char* arena, size_t arena_bytes) { return (P2PFlags*)(arena + arena_bytes - 256 + 128); }
-
 extern "C" int vof2d_p2p_export(VofCtx* c, void* handle64, int64_t* nrows, int64_t* arena_bytes) {
     CHECK_CTX(c);
     if (!c->own_arena) return fail(VOF_ESTATE, "p2p export needs a library-owned (cudaMalloc) arena");
@@ -1168,29 +1147,7 @@ extern "C" int vof2d_p2p_connect(VofCtx* c, int side, const void* handle64, void
     if (side != 0 && side != 1) return fail(VOF_EINVAL, "side must be 0 or 1");
     if ((side == 0 && c->has_lo) || (side == 1 && c->has_hi)) return fail(VOF_ESTATE, "side %d is a physical wall", side);
     CU(cudaSetDevice(c->device));
-    if (same_process_arena) { c->peer_arena[side] = (char*)same_process_arena; c->peer_ipc[side] = false; }
-    else {
-        if (!handle64) return fail(VOF_EINVAL, "null IPC handle");
-        cudaIpcMemHandle_t h;
-        memcpy(&h, handle64, 64);
-        void* ptr = nullptr;
-        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
-        c->peer_arena[side] = (char*)ptr; c->peer_ipc[side] = true;
-    }
-    c->peer_nrows[side] = peer_nrows;
-    // CUDA loads kernels lazily and a first-use load may wait for the device to go idle: with a flag-waiting kernel
-    // already spinning that is a deadlock.  Load the hand-shake kernels now, while nothing waits.
-    cudaFuncAttributes fa;
-    CU(cudaFuncGetAttributes(&fa, k_p2p_signal));
-    CU(cudaFuncGetAttributes(&fa, k_p2p_wait));
-    CU(cudaFuncGetAttributes(&fa, k_p2p_push));
-    k_p2p_signal<<<1, 1, 0, c->stream>>>(nullptr, nullptr, 0u, nullptr, nullptr, 0u);
-    k_p2p_wait<<<1, 1, 0, c->stream>>>(nullptr, nullptr, 0u, &flags_of(c->arena, c->arena_bytes)->timeout, nullptr, nullptr, 0u,
-                                       &flags_of(c->arena, c->arena_bytes)->mismatch);
-    P2PPush none; memset(&none, 0, sizeof(none));
-    k_p2p_push<<<dim3(1, 8), 256, 0, c->stream>>>(none, 0);
-    CU(cudaStreamSynchronize(c->stream));
-    return VOF_OK;
+    return p2p_connect(c->p2p, side, handle64, same_process_arena, peer_nrows, arena_bytes_for_rows(c, peer_nrows), c->stream);
 }
 
 extern "C" int vof2d_p2p_arena(VofCtx* c, void** arena) { CHECK_CTX(c); if (arena) *arena = c->arena; return VOF_OK; }
@@ -1199,52 +1156,36 @@ extern "C" int vof2d_halo_exchange_p2p(VofCtx* c) {
     CHECK_CTX(c);
     const bool nlo = !c->has_lo, nhi = !c->has_hi;
     if (!nlo && !nhi) return VOF_OK;
-    if ((nlo && !c->peer_arena[0]) || (nhi && !c->peer_arena[1])) return fail(VOF_ESTATE, "vof2d_p2p_connect was not called for every neighbour");
     CU(cudaSetDevice(c->device));
-    Span span_(c, VOF_K_HALO, 5);
-    const unsigned int e = ++c->p2p_epoch;
-    P2PFlags* mine = flags_of(c->arena, c->arena_bytes);
-    P2PFlags* plo = nlo ? flags_of(c->peer_arena[0], arena_bytes_for_rows(c, c->peer_nrows[0])) : nullptr;
-    P2PFlags* phi = nhi ? flags_of(c->peer_arena[1], arena_bytes_for_rows(c, c->peer_nrows[1])) : nullptr;
-    // I am the lower neighbour's upper side (index 1) and the upper neighbour's lower side (index 0)
-    const unsigned int cur = (unsigned int)(c->F_cur | (c->p_cur << 1));
-    k_p2p_signal<<<1, 1, 0, c->stream>>>(plo ? &plo->done_from[1] : nullptr, phi ? &phi->done_from[0] : nullptr, e,
-                                         plo ? &plo->cur_from[1] : nullptr, phi ? &phi->cur_from[0] : nullptr, cur);
-    k_p2p_wait<<<1, 1, 0, c->stream>>>(nlo ? &mine->done_from[0] : nullptr, nhi ? &mine->done_from[1] : nullptr, e, &mine->timeout,
-                                       nlo ? &mine->cur_from[0] : nullptr, nhi ? &mine->cur_from[1] : nullptr, cur, &mine->mismatch);
-    P2PPush a;
-    memset(&a, 0, sizeof(a));
+    Span span_(c, VOF_K_HALO, 1);
+    P2PTable t;
+    memset(&t, 0, sizeof(t));
     const int H = c->H, n = c->g.nrows, P = c->g.pitch;
     const int fields[4] = {BUF_U, BUF_V, c->p_cur ? BUF_P1 : BUF_P0, c->F_cur ? BUF_F1 : BUF_F0};
+    const long long count4 = (long long)H * P / 4;     // pitch is a multiple of 32 floats
     for (int f = 0; f < 4; ++f) {
         const size_t my_off = c->field_bytes * fields[f];
         if (nlo) {   // my rows [H, 2H) -> lower neighbour's rows [n' - H, n')
-            const size_t pfb = field_stride_bytes((int)c->peer_nrows[0], P);
-            a.src[f * 2 + 0] = (const float4*)(c->arena + my_off + (size_t)H * P * sizeof(float));
-            a.dst[f * 2 + 0] = (float4*)(c->peer_arena[0] + pfb * fields[f] + (size_t)(c->peer_nrows[0] - H) * P * sizeof(float));
+            const size_t pfb = field_stride_bytes((int)c->p2p.peer_nrows[0], P);
+            t.src[t.n] = (const float4*)(c->arena + my_off + (size_t)H * P * sizeof(float));
+            t.dst[t.n] = (float4*)(c->p2p.peer_arena[0] + pfb * fields[f] + (size_t)(c->p2p.peer_nrows[0] - H) * P * sizeof(float));
+            t.count4[t.n++] = count4;
         }
         if (nhi) {   // my rows [n - 2H, n - H) -> upper neighbour's rows [0, H)
-            const size_t pfb = field_stride_bytes((int)c->peer_nrows[1], P);
-            a.src[f * 2 + 1] = (const float4*)(c->arena + my_off + (size_t)(n - 2 * H) * P * sizeof(float));
-            a.dst[f * 2 + 1] = (float4*)(c->peer_arena[1] + pfb * fields[f]);
+            const size_t pfb = field_stride_bytes((int)c->p2p.peer_nrows[1], P);
+            t.src[t.n] = (const float4*)(c->arena + my_off + (size_t)(n - 2 * H) * P * sizeof(float));
+            t.dst[t.n] = (float4*)(c->p2p.peer_arena[1] + pfb * fields[f]);
+            t.count4[t.n++] = count4;
         }
     }
-    const long long count4 = (long long)H * P / 4;     // pitch is a multiple of 32 floats
-    k_p2p_push<<<dim3(32, 8), 256, 0, c->stream>>>(a, count4);
-    k_p2p_signal<<<1, 1, 0, c->stream>>>(plo ? &plo->data_from[1] : nullptr, phi ? &phi->data_from[0] : nullptr, e, nullptr, nullptr, 0u);
-    k_p2p_wait<<<1, 1, 0, c->stream>>>(nlo ? &mine->data_from[0] : nullptr, nhi ? &mine->data_from[1] : nullptr, e, &mine->timeout,
-                                       nullptr, nullptr, 0u, &mine->mismatch);
-    return launch_ok("p2p halo exchange");
+    if ((nlo && !c->p2p.peer_arena[0]) || (nhi && !c->p2p.peer_arena[1])) return fail(VOF_ESTATE, "vof2d_p2p_connect was not called for every neighbour");
+    return p2p_exchange(c->p2p, c->arena, c->arena_bytes, nlo, nhi, (unsigned int)(c->F_cur | (c->p_cur << 1)), t, c->stream);
 }
 
 extern "C" int vof2d_p2p_status(VofCtx* c, int* timed_out_epoch) {
     CHECK_CTX(c);
     CU(cudaSetDevice(c->device));
-    unsigned int t = 0;
-    CU(cudaMemcpyAsync(&t, &flags_of(c->arena, c->arena_bytes)->timeout, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if (timed_out_epoch) *timed_out_epoch = (int)t;
-    return VOF_OK;
+    return p2p_check(c->arena, c->arena_bytes, c->stream, timed_out_epoch, false);
 }
 
 // Error (VOF_ESTATE) if any halo exchange so far gave up waiting for a neighbour (20 s watchdog) or found the
@@ -1252,12 +1193,7 @@ extern "C" int vof2d_p2p_status(VofCtx* c, int* timed_out_epoch) {
 extern "C" int vof2d_p2p_check(VofCtx* c) {
     CHECK_CTX(c);
     CU(cudaSetDevice(c->device));
-    unsigned int t[2] = {0, 0};
-    CU(cudaMemcpyAsync(t, &flags_of(c->arena, c->arena_bytes)->timeout, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if (t[0]) return fail(VOF_ESTATE, "halo exchange %u timed out waiting for a neighbour (20 s); the halo rows since then are stale", t[0]);
-    if (t[1]) return fail(VOF_ESTATE, "halo exchange %u: a neighbour holds F / p in the other ping-pong buffer (ranks are not in lockstep)", t[1]);
-    return VOF_OK;
+    return p2p_check(c->arena, c->arena_bytes, c->stream);
 }
 
 // ------------------------------------------------------------------------------------

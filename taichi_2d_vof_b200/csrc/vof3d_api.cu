@@ -1,6 +1,7 @@
 // libvof C ABI, 3-D context (include/vof.h, vof3d_*): replaces the loop body of 3dvof.py:598-623.
 #include "vof_host_common.h"
 #include "vof3d_kernels.cuh"
+#include "vof_p2p.cuh"
 
 using namespace vof;
 using vofhost::cdiv;
@@ -36,6 +37,8 @@ struct Vof3Ctx {
     int opt_jac_smem;          // 1: k3_jacobi6 (j-neighbours through shared memory: measured 10 % slower), 0 (default): k3_jacobi5
     bool bc_clean;             // every ghost cell is what set_BC would write now (true after a whole step; any other writer clears it)
     int opt_gen2;              // 1 (default): second-generation kernels, 0: first generation (same bits)
+    P2PEndpoint p2p;           // neighbour arenas (lower / upper) mapped for the NVLink peer-store halo exchange
+    vofhost::AsyncGet* aget;   // non-stalling field read for the VTK export path (vof3d_field_get_async)
     float* F() { return buf[F_cur ? B3_F1 : B3_F0]; }
     float* F_alt() { return buf[F_cur ? B3_F0 : B3_F1]; }
     float* p() { return buf[p_cur ? B3_P1 : B3_P0]; }
@@ -178,6 +181,8 @@ extern "C" int vof3d_destroy(Vof3Ctx* c) {
     if (!c) return VOF_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    p2p_close(c->p2p);
+    if (c->aget) { vofhost::async_get_free(*c->aget); delete c->aget; }
     if (c->arena) cudaFree(c->arena);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -480,6 +485,23 @@ extern "C" int vof3d_field_get(Vof3Ctx* c, int field, float* host_dst) {
     CU(cudaStreamSynchronize(c->stream));
     return VOF_OK;
 }
+// non-stalling read for the VTK export (3dvof.py:624-627): see vof2d_field_get_async
+extern "C" int vof3d_field_get_async(Vof3Ctx* c, int field, float* host_dst) {
+    CHECK_CTX(c);
+    float* d = field3(c, field);
+    if (!d || !host_dst) return fail(VOF_EINVAL, "bad field id %d or null destination", field);
+    CU(cudaSetDevice(c->device));
+    if (!c->aget) c->aget = new vofhost::AsyncGet();
+    return vofhost::async_get_begin(*c->aget, c->stream, d - kColOff, c->field_bytes, (size_t)c->g.pk * sizeof(float),
+                                    (size_t)(c->g.nz + 2) * sizeof(float), (size_t)c->g.nrows * (c->g.ny + 2),
+                                    (size_t)kColOff * sizeof(float), host_dst);
+}
+extern "C" int vof3d_field_get_wait(Vof3Ctx* c) {
+    CHECK_CTX(c);
+    if (!c->aget) return VOF_OK;
+    CU(cudaSetDevice(c->device));
+    return vofhost::async_get_wait(*c->aget);
+}
 extern "C" int vof3d_field_set(Vof3Ctx* c, int field, const float* host_src) {
     CHECK_CTX(c); c->bc_clean = false;
     float* d = field3(c, field);
@@ -526,6 +548,67 @@ extern "C" int vof3d_halo_push(Vof3Ctx* c, int field, int side, float* peer_halo
     CU(cudaSetDevice(c->device));
     CU(cudaMemcpyAsync(peer_halo_dst, src, (size_t)n * sizeof(float), cudaMemcpyDefault, c->stream));
     return VOF_OK;
+}
+
+// ---- NVLink peer-to-peer exchange of the halo planes (vof_p2p.cuh): u, v, w, p, F in ONE kernel per step
+static size_t arena_bytes_for_planes3(const Vof3Ctx* c, long long nrows) {
+    Grid3 g = c->g; g.nrows = (int)nrows;
+    const size_t xyz = ((size_t)(c->P.nx + c->P.ny + c->P.nz + 9) * sizeof(float) + 255) / 256 * 256;
+    return field_bytes3(g) * B3_COUNT + xyz + 256;
+}
+extern "C" int vof3d_p2p_export(Vof3Ctx* c, void* handle64, int64_t* nrows, int64_t* arena_bytes) {
+    CHECK_CTX(c);
+    CU(cudaSetDevice(c->device));
+    if (handle64) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, c->arena));
+        memcpy(handle64, &h, 64);
+    }
+    if (nrows) *nrows = c->g.nrows;
+    if (arena_bytes) *arena_bytes = (int64_t)c->arena_bytes;
+    return VOF_OK;
+}
+extern "C" int vof3d_p2p_connect(Vof3Ctx* c, int side, const void* handle64, void* same_process_arena, int64_t peer_nrows) {
+    CHECK_CTX(c);
+    if (side != 0 && side != 1) return fail(VOF_EINVAL, "side must be 0 or 1");
+    if ((side == 0 && c->has_lo) || (side == 1 && c->has_hi)) return fail(VOF_ESTATE, "side %d is a physical wall", side);
+    CU(cudaSetDevice(c->device));
+    return p2p_connect(c->p2p, side, handle64, same_process_arena, peer_nrows, arena_bytes_for_planes3(c, peer_nrows), c->stream);
+}
+extern "C" int vof3d_p2p_arena(Vof3Ctx* c, void** arena) { CHECK_CTX(c); if (arena) *arena = c->arena; return VOF_OK; }
+extern "C" int vof3d_halo_exchange_p2p(Vof3Ctx* c) {
+    CHECK_CTX(c);
+    const bool nlo = !c->has_lo, nhi = !c->has_hi;
+    if (!nlo && !nhi) return VOF_OK;
+    if ((nlo && !c->p2p.peer_arena[0]) || (nhi && !c->p2p.peer_arena[1])) return fail(VOF_ESTATE, "vof3d_p2p_connect was not called for every neighbour");
+    CU(cudaSetDevice(c->device));
+    c->bc_clean = false;
+    ++c->launches;
+    P2PTable t;
+    memset(&t, 0, sizeof(t));
+    const int H = c->H, n = c->g.nrows;
+    const size_t plane_bytes = (size_t)c->g.pj * sizeof(float);
+    const int fields[5] = {B3_U, B3_V, B3_W, c->p_cur ? B3_P1 : B3_P0, c->F_cur ? B3_F1 : B3_F0};
+    const long long count4 = (long long)H * c->g.pj / 4;       // pk (hence pj) is a multiple of 32 floats
+    for (int f = 0; f < 5; ++f) {
+        const size_t my_off = c->field_bytes * fields[f];
+        for (int sd = 0; sd < 2; ++sd) {
+            if (!(sd == 0 ? nlo : nhi)) continue;
+            Grid3 pg = c->g; pg.nrows = (int)c->p2p.peer_nrows[sd];
+            const size_t pfb = field_bytes3(pg);
+            const long long src_plane = sd == 0 ? H : n - 2 * H;                     // my boundary planes
+            const long long dst_plane = sd == 0 ? c->p2p.peer_nrows[0] - H : 0;      // the neighbour's halo planes
+            t.src[t.n] = (const float4*)(c->arena + my_off + (size_t)src_plane * plane_bytes);
+            t.dst[t.n] = (float4*)(c->p2p.peer_arena[sd] + pfb * fields[f] + (size_t)dst_plane * plane_bytes);
+            t.count4[t.n++] = count4;
+        }
+    }
+    return p2p_exchange(c->p2p, c->arena, c->arena_bytes, nlo, nhi, (unsigned int)(c->F_cur | (c->p_cur << 1)), t, c->stream);
+}
+extern "C" int vof3d_p2p_check(Vof3Ctx* c) {
+    CHECK_CTX(c);
+    CU(cudaSetDevice(c->device));
+    return p2p_check(c->arena, c->arena_bytes, c->stream);
 }
 
 extern "C" int vof3d_set_option(Vof3Ctx* c, int option, int value) {

@@ -45,6 +45,7 @@ inline void node_coords(std::vector<float>& x, int n, double L) {
     x[(size_t)n + 2] = (float)L;
 }
 
+
 }  // namespace vofhost
 
 #define CU(call)                                                                             \
@@ -56,3 +57,54 @@ inline void node_coords(std::vector<float>& x, int n, double L) {
 #define CHECK_CTX(c) \
     do { if (!(c)) return vofhost::fail(VOF_EINVAL, "null context"); } while (0)
 #define TRY(x) do { int rc_ = (x); if (rc_ != VOF_OK) return rc_; } while (0)
+
+// Non-stalling device -> host read of one field (the -s / VTK output path, 2dvof.py:565, 3dvof.py:627): the field is
+// snapshotted device-to-device on the compute stream (268 MB at 8192^2: ~0.1 ms), and the snapshot travels to the
+// (pinned) host buffer on a side stream while the time loop goes on.  One read in flight per context.
+namespace vofhost {
+struct AsyncGet {
+    float* snap = nullptr;
+    size_t snap_bytes = 0;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ready = nullptr, done = nullptr;
+    bool pending = false;
+};
+// src_row0: start of the pitched field (first row, pad columns included); the host array is dense rows of width_bytes
+inline int async_get_begin(AsyncGet& a, cudaStream_t compute, const float* src_row0, size_t field_bytes, size_t pitch_bytes,
+                           size_t width_bytes, size_t rows, size_t col_off_bytes, float* host_dst) {
+    if (!a.side) {
+        CU(cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&a.ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming));
+    }
+    if (a.snap_bytes < field_bytes) {
+        if (a.pending) CU(cudaEventSynchronize(a.done));
+        if (a.snap) cudaFree(a.snap);
+        a.snap = nullptr; a.snap_bytes = 0;
+        if (cudaMalloc((void**)&a.snap, field_bytes) != cudaSuccess)
+            return fail(VOF_ENOMEM, "cudaMalloc(%zu bytes) for the output snapshot failed", field_bytes);
+        a.snap_bytes = field_bytes;
+    }
+    if (a.pending) CU(cudaStreamWaitEvent(compute, a.done, 0));     // the previous read still owns the snapshot
+    CU(cudaMemcpyAsync(a.snap, src_row0, field_bytes, cudaMemcpyDeviceToDevice, compute));
+    CU(cudaEventRecord(a.ready, compute));
+    CU(cudaStreamWaitEvent(a.side, a.ready, 0));
+    CU(cudaMemcpy2DAsync(host_dst, width_bytes, (const char*)a.snap + col_off_bytes, pitch_bytes, width_bytes, rows,
+                         cudaMemcpyDeviceToHost, a.side));
+    CU(cudaEventRecord(a.done, a.side));
+    a.pending = true;
+    return VOF_OK;
+}
+inline int async_get_wait(AsyncGet& a) {
+    if (a.pending) { CU(cudaEventSynchronize(a.done)); a.pending = false; }
+    return VOF_OK;
+}
+inline void async_get_free(AsyncGet& a) {
+    if (a.pending) cudaEventSynchronize(a.done);
+    if (a.snap) cudaFree(a.snap);
+    if (a.ready) cudaEventDestroy(a.ready);
+    if (a.done) cudaEventDestroy(a.done);
+    if (a.side) cudaStreamDestroy(a.side);
+    a = AsyncGet();
+}
+}  // namespace vofhost

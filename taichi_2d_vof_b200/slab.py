@@ -9,8 +9,11 @@ the few halo rows redundantly, and exchanges u, v, p, F ONCE per step (4 fields 
 pitched rows per neighbour) instead of once per sweep.  Physical-wall logic applies only on the
 first / last rank; interior ranks see their neighbours' rows as ordinary cells.
 
-Transport: ``torch.distributed`` P2P (NCCL over NVLink on the GPU box; gloo on CPU for the
-host-logic tests).  ``partition`` / ``exchange`` are pure host logic and device-agnostic.
+Transport (2-D and 3-D): ``p2p`` = peer stores over NVLink by one fused kernel per step (csrc/vof_p2p.cuh: the
+neighbours' arenas are mapped with CUDA IPC, hand-shakes are device-side flags, no NCCL call and no host
+synchronisation on the data path); ``nccl`` = ``torch.distributed`` batched isend / irecv (gloo on CPU for the
+host-logic tests).  The only collective is the diagnostics reduction (one all-gather of a 4-vector, when asked).
+``partition`` / ``exchange`` are pure host logic and device-agnostic.
 """
 from __future__ import annotations
 
@@ -87,9 +90,11 @@ class SlabSolver2D:
         self.solver = solver_cls(params, stream=self.stream)
         self.halo = self.solver.halo
         self._views = None
+        self._steps = 0
+        self.check_every = 256          # steps between p2p health checks (each one synchronises the stream); 0 = never
+        import inspect
+        self._diag_takes_residual = "residual" in inspect.signature(self.solver.diagnostics).parameters
         self.transport = transport if nranks > 1 else "none"
-        if self.transport == "p2p" and not hasattr(self.solver, "p2p_export"):
-            self.transport = "nccl"     # the 3-D context has no peer-store exchange yet
         if self.transport == "p2p":
             # map the neighbours' arenas (CUDA IPC): halo rows are then stored straight over NVLink by
             # vof2d_halo_exchange_p2p, hand-shaking through device-side flags -- no NCCL call per step
@@ -138,12 +143,143 @@ class SlabSolver2D:
     def step(self):
         self.exchange_halos()
         self.solver.step()
+        self._steps += 1
+        if self.check_every and self._steps % self.check_every == 0:
+            self.check()
+
+    def run(self, nsteps: int):
+        if self.nranks == 1 and hasattr(self.solver, "run"):
+            self.solver.run(nsteps)         # one GPU: CUDA-graph replay of whole steps
+            return
+        for _ in range(nsteps):
+            self.step()
+
+    @property
+    def istep(self):
+        return self.solver.istep
+
+    def check(self):
+        """Raises VofError if a peer-store halo exchange timed out (dead neighbour) or the ranks fell out of lockstep;
+        synchronises this rank's stream.  Called by diagnostics() and every ``check_every`` steps."""
+        if self.transport == "p2p":
+            self.solver.p2p_check()
 
     def owned(self, name):
         """This rank's owned interior rows of a field, as numpy (rows lo..hi, all columns)."""
         a = getattr(self.solver, name).to_numpy()
         H = self.solver.halo if self.nranks > 1 else 1
         return a[H:a.shape[0] - H]
+
+    def diagnostics(self, residual=True):
+        """Global diagnostics of the decomposed run ("one allreduce per step of {sum F (fp64), max CFL,
+        Jacobi residual, Courant count}"; the reference's only diagnostic is the Courant print, 2dvof.py:274-280).
+        Every rank reduces its OWNED rows on the device (warp shuffles + one atomic per block), then one collective
+        combines the per-rank 4-vectors: sum of volumes and Courant counts, max of CFL and residual."""
+        self.check()
+        d = self.solver.diagnostics(residual=residual) if self._diag_takes_residual else self.solver.diagnostics()
+        if self.nranks == 1:
+            return d
+        import torch
+        vec = torch.tensor([d["mass"], d["max_cfl"], d.get("residual") or 0.0, float(d["courant_count"])],
+                           dtype=torch.float64, device=self._device())
+        out = torch.empty((self.nranks, 4), dtype=torch.float64, device=vec.device)
+        self.dist.all_gather_into_tensor(out, vec)
+        out = out.cpu()
+        res = {"mass": float(out[:, 0].sum()), "max_cfl": float(out[:, 1].max()), "courant_count": int(out[:, 3].sum()),
+               "mass_per_rank": [float(x) for x in out[:, 0]]}
+        if "residual" in d:
+            res["residual"] = float(out[:, 2].max()) if residual else None
+        return res
+
+    def mass(self):
+        return self.diagnostics(residual=False)["mass"]
+
+    def _device(self):
+        import torch
+        if self.dist is not None and self.dist.get_backend() == "gloo":
+            return torch.device("cpu")
+        return torch.device(f"cuda:{self.solver.device}") if hasattr(self.solver, "device") else torch.device("cuda")
+
+    def gather(self, name):
+        """The global field on rank 0 (None elsewhere): owned rows of every rank plus the two physical ghost rows."""
+        import numpy as np
+        import torch
+        a = getattr(self.solver, name).to_numpy()
+        if self.nranks == 1:
+            return a
+        H = self.solver.halo
+        lo = H - (1 if self.rank == 0 else 0)
+        hi = a.shape[0] - H + (1 if self.rank == self.nranks - 1 else 0)
+        mine = np.ascontiguousarray(a[lo:hi])
+        tall = max(h - l + 1 for l, h in self.parts) + 1
+        dev = self._device()
+        pad = torch.zeros((tall,) + mine.shape[1:], dtype=torch.float32, device=dev)
+        pad[: mine.shape[0]] = torch.from_numpy(mine).to(dev)
+        outs = [torch.empty_like(pad) for _ in range(self.nranks)] if self.rank == 0 else None
+        self.dist.gather(pad, outs, dst=0)
+        if self.rank != 0:
+            return None
+        rows = []
+        for r, (l, h) in enumerate(self.parts):
+            n = h - l + 1 + (1 if r == 0 else 0) + (1 if r == self.nranks - 1 else 0)
+            rows.append(outs[r][:n].cpu().numpy())
+        return np.concatenate(rows, axis=0)
+
+    def scatter(self, name, global_array):
+        """Load this rank's local rows (owned + halo) of a field from the global array (every rank passes the same array)."""
+        import numpy as np
+        s = self.solver
+        if self.nranks == 1:
+            getattr(s, name).from_numpy(global_array)
+            return
+        gi0 = s.lo - s.halo
+        loc = np.zeros((s.nrows,) + tuple(global_array.shape[1:]), np.float32)
+        g0, g1 = max(gi0, 0), min(gi0 + s.nrows, global_array.shape[0])
+        loc[g0 - gi0:g1 - gi0] = global_array[g0:g1]
+        getattr(s, name).from_numpy(loc)
+
+
+def slab_parity_check(dist, rank, world, device, nx=2048, ny=640, steps=6, ic=3, transport="p2p", three_d=False, n=96):
+    """Correctness signal for multi-GPU runs (bench.py, tests): every rank steps its slab of a small global problem,
+    rank 0 also runs the whole domain on its own GPU, and every owned row must equal it bit for bit.  Returns a dict
+    on rank 0 (None elsewhere)."""
+    import numpy as np
+    if three_d:
+        from .solver3d import VofSolver3D as cls, reference_params3d
+        L = 0.1 * n / 200
+
+        def params_fn(slab, halo, device):
+            return reference_params3d(nx=n, ny=n, nz=n, Lx=L, Ly=L, Lz=L, slab=slab, halo=halo, device=device)
+        nx, fields, ic = n, ("F", "u", "v", "w", "p"), 1
+    else:
+        from .solver2d import VofSolver2D as cls, reference_params
+
+        def params_fn(slab, halo, device):
+            return reference_params(nx=nx, ny=ny, Lx=0.1 * nx / 200, Ly=0.1 * ny / 200, slab=slab, halo=halo, device=device)
+        fields = ("F", "u", "v", "p")
+    s = SlabSolver2D(params_fn, nx, rank, world, dist=dist, device=device, transport=transport, solver_cls=cls, halo_fields=fields)
+    s.set_init_F(ic)
+    s.run(steps)
+    d = s.diagnostics(residual=False)
+    full = None
+    if rank == 0:
+        full = cls(params_fn(None, 0, device))
+        full.set_init_F(ic)
+        for _ in range(steps):
+            full.step()
+    bad = {}
+    for name in fields:
+        g = s.gather(name)
+        if rank == 0:
+            ref = getattr(full, name).to_numpy()
+            bad[name] = int(np.count_nonzero(g != ref))
+    if rank != 0:
+        return None
+    m_single = full.mass()
+    return {"problem": (f"{n}^3 dam break" if three_d else f"{nx} x {ny} -ic {ic}") + f", {steps} steps, {world} slabs vs one GPU",
+            "transport": s.transport, "fields": list(fields), "cells_differing": bad, "identical": all(v == 0 for v in bad.values()),
+            "global_volume_allreduced": d["mass"], "single_gpu_volume": m_single,
+            "volume_rel_diff": abs(d["mass"] - m_single) / m_single if m_single else 0.0}
 
 
 class LocalSlabGroup:

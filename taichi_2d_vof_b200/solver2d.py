@@ -57,6 +57,17 @@ class Field:
         check(self._s._L.vof2d_field_get(self._s._h, self.fid, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def to_numpy_async(self, out) -> "Field":
+        """Non-stalling read into ``out`` (use ``_lib.pinned_empty``): returns at once, the time loop may go on;
+        ``wait()`` makes ``out`` valid.  One read in flight per solver."""
+        if out.shape != self.shape or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError(f"field {self.name}: out must be C-contiguous float32 {self.shape}")
+        check(self._s._L.vof2d_field_get_async(self._s._h, self.fid, out.ctypes.data_as(C.c_void_p)))
+        return self
+
+    def wait(self):
+        check(self._s._L.vof2d_field_get_wait(self._s._h))
+
     def from_numpy(self, arr):
         a = np.ascontiguousarray(arr, dtype=np.float32)
         if a.shape != self.shape:

@@ -42,6 +42,16 @@ class Field3:
         check(self._s._L.vof3d_field_get(self._s._h, self.fid, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def to_numpy_async(self, out):
+        """Non-stalling read into a pinned array (``_lib.pinned_empty``); ``wait()`` makes it valid."""
+        if out.shape != self.shape or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError(f"field {self.name}: out must be C-contiguous float32 {self.shape}")
+        check(self._s._L.vof3d_field_get_async(self._s._h, self.fid, out.ctypes.data_as(C.c_void_p)))
+        return self
+
+    def wait(self):
+        check(self._s._L.vof3d_field_get_wait(self._s._h))
+
     def from_numpy(self, arr):
         a = np.ascontiguousarray(arr, dtype=np.float32)
         if a.shape != self.shape:
@@ -136,6 +146,28 @@ class VofSolver3D:
 
     def halo_push(self, name, side, peer_dst):
         check(self._L.vof3d_halo_push(self._h, _lib.FIELD_IDS[name], side, C.c_void_p(peer_dst)))
+
+    # ---- NVLink peer-store halo exchange (same protocol as the 2-D context)
+    def p2p_export(self):
+        buf = (C.c_ubyte * 64)()
+        n, nb = C.c_int64(), C.c_int64()
+        check(self._L.vof3d_p2p_export(self._h, buf, C.byref(n), C.byref(nb)))
+        return bytes(buf), n.value
+
+    def p2p_arena(self):
+        a = C.c_void_p()
+        check(self._L.vof3d_p2p_arena(self._h, C.byref(a)))
+        return a.value
+
+    def p2p_connect(self, side, handle=None, arena_ptr=None, peer_nrows=0):
+        hb = (C.c_ubyte * 64).from_buffer_copy(handle) if handle is not None else None
+        check(self._L.vof3d_p2p_connect(self._h, side, hb, C.c_void_p(arena_ptr) if arena_ptr else None, int(peer_nrows)))
+
+    def halo_exchange_p2p(self):
+        check(self._L.vof3d_halo_exchange_p2p(self._h))
+
+    def p2p_check(self):
+        check(self._L.vof3d_p2p_check(self._h))
 
 
 def _bind(name):

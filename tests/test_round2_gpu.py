@@ -103,11 +103,32 @@ def test_all_rank_slabs_equal_single_gpu_2d(built_lib):
     assert rc == 0 and "MGPU PARITY OK" in out, out[-3000:]
 
 
-def test_two_rank_slabs_equal_single_gpu_3d(built_lib):
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+def test_two_rank_slabs_equal_single_gpu_3d(built_lib, transport):
     if _ngpu() < 2:
         pytest.skip("needs >= 2 GPUs")
-    rc, out = _torchrun("mgpu_parity3d.py", 2, 29614, "96", "7")
+    rc, out = _torchrun("mgpu_parity3d.py", 2, 29614 if transport == "p2p" else 29615, "96", "7", env={"VOF_TRANSPORT": transport})
     assert rc == 0 and "MGPU 3D PARITY OK" in out, out[-3000:]
+
+
+@pytest.mark.parametrize("nslabs", [2, 3])
+def test_plane_slabs_p2p_equal_full_domain_3d(built_lib, nslabs):
+    """The fused peer-store exchange kernel for the 3-D context, slabs on one device (plain pointers instead of CUDA IPC)."""
+    from taichi_2d_vof_b200 import VofSolver3D, reference_params3d
+    from taichi_2d_vof_b200.slab import LocalSlabGroup
+    nx, ny, nz = 72, 20, 36
+
+    def params_fn(slab, halo, device):
+        return reference_params3d(nx=nx, ny=ny, nz=nz, Lx=0.036, Ly=0.01, Lz=0.018, slab=slab, halo=halo, device=device)
+
+    full = VofSolver3D(params_fn(None, 0, 0)); full.set_init_F(1)
+    grp = LocalSlabGroup(params_fn, nx, nslabs, p2p=True, solver_cls=VofSolver3D, halo_fields=("F", "u", "v", "w", "p")); grp.set_init_F(1)
+    for step in range(9):
+        full.step(); grp.step()
+    for s in grp.solvers:
+        s.p2p_check()
+    for k in ("F", "u", "v", "w", "p"):
+        _same(grp.gather(k), getattr(full, k).to_numpy(), f"3-D {nslabs} slabs (p2p) field {k}")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -238,3 +259,73 @@ def test_create_failure_does_not_leak(built_lib):
     torch.cuda.empty_cache()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 64 << 20
+
+
+# ----------------------------------------------------------------------------------------------
+# the on-disk output of `2dvof.py -s` / `3dvof.py`, through the drop-in scripts at the repo root
+# ----------------------------------------------------------------------------------------------
+def test_2dvof_script_dash_s_writes_the_reference_steps(built_lib, tmp_path):
+    """`python 2dvof.py -ic 3 -s` (the reference's default grid, 200 steps, headless): the F arrays it writes every
+    100 steps (output/%06d-f.npy, 2dvof.py:563-571) equal the oracle's F at those steps, every element."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "2dvof.py"), "-ic", "3", "-s", "--steps", "200"], cwd=tmp_path,
+                       env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert ">>> Grid resolution: 200 x 200, dt = 4.00e-06" in r.stdout
+    o = Vof2DCOracle(Vof2DParams()); o.set_init_F(3)
+    for count in (0, 1):
+        o.run(100)
+        F = np.load(tmp_path / "output" / f"{count:06d}-f.npy")
+        _same(F, o.F, f"2dvof.py -s, file {count:06d}-f.npy")
+
+
+def test_3dvof_script_writes_vtr_with_the_oracle_field(built_lib, tmp_path):
+    """`python 3dvof.py` on a small grid, 100 steps: output/step-00100.vtr (3dvof.py:624-627) holds the oracle's F."""
+    from taichi_2d_vof_b200.vtk import read_vtr_arrays
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "3dvof.py"), "--nx", "24", "--ny", "20", "--nz", "28", "--scaled",
+                        "--steps", "100"], cwd=tmp_path, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert ">>> Exporting step-00100 result..." in r.stdout
+    P = Vof3DParams(nx=24, ny=20, nz=28, Lx=0.012, Ly=0.01, Lz=0.014)
+    o = Vof3DCOracle(P); o.set_init_F(1); o.run(100)
+    back = read_vtr_arrays(str(tmp_path / "output" / "step-00100.vtr"))
+    assert back["shape"] == (26, 22, 30)
+    _same(back["VOF"], o.F, "3dvof.py export, step-00100.vtr point data VOF")
+
+
+def test_async_field_read_does_not_block_and_is_a_snapshot(built_lib):
+    """vof2d_field_get_async: returns at once, the loop continues on the compute stream, and the array that arrives is the
+    field at the time of the call (not a later state)."""
+    import time
+    from taichi_2d_vof_b200 import VofSolver2D, _lib, scaled_params
+    s = VofSolver2D(scaled_params(4096)); s.set_init_F(3); s.run(10)
+    want = s.F.to_numpy()
+    out = _lib.pinned_empty(want.shape)
+    s.synchronize()
+    t0 = time.perf_counter()
+    s.F.to_numpy_async(out)
+    t_call = time.perf_counter() - t0
+    s.run(40)                                        # 40 more steps are queued behind the snapshot, none behind the copy
+    s.F.wait()
+    assert np.array_equal(out, want)
+    assert t_call < 0.02, f"the async read took {t_call * 1e3:.1f} ms to return"
+    assert not np.array_equal(s.F.to_numpy(), want)
+    _lib.pinned_free(out)
+
+
+def test_driver_gpus_flag_equals_single_gpu(built_lib, tmp_path):
+    """`2dvof.py --gpus 2 --dump` == `2dvof.py --dump` (row slabs + NVLink peer stores behind the drop-in CLI)."""
+    if _ngpu() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    common = ["-ic", "3", "--nx", "512", "--ny", "384", "--scaled", "--steps", "30", "-s", "--nstep", "10"]
+    for tag, extra in (("one", []), ("two", ["--gpus", "2"])):
+        d = tmp_path / tag
+        d.mkdir()
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "2dvof.py"), *common, *extra, "--dump", "state.npz"], cwd=d,
+                           env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+    a, b = np.load(tmp_path / "one" / "state.npz"), np.load(tmp_path / "two" / "state.npz")
+    for k in ("u", "v", "p", "F"):
+        _same(b[k], a[k], f"--gpus 2 vs one GPU, field {k}")
+    for count in range(3):
+        _same(np.load(tmp_path / "two" / "output" / f"{count:06d}-f.npy"), np.load(tmp_path / "one" / "output" / f"{count:06d}-f.npy"),
+              f"--gpus 2 -s output {count}")
