@@ -54,12 +54,22 @@ def lib():
         L.ovof2d_set_init_F.argtypes = [C.c_void_p, C.c_int]
         L.ovof2d_run.argtypes = [C.c_void_p, C.c_int]
         L.ovof2d_threads.restype = C.c_int
+        L.ovof_set_threads.argtypes = [C.c_int]
+        L.ovof_set_threads.restype = None
         for name in ("destroy", "set_BC", "cal_nu_rho", "get_normal_young", "advect_upwind", "solve_p_jacobi",
                      "update_uv", "fct_x_sweep", "fct_y_sweep", "post_process_f", "solve_VOF_rudman", "step"):
             getattr(L, "ovof2d_" + name).argtypes = [C.c_void_p]
             getattr(L, "ovof2d_" + name).restype = None
         _LIB = L
     return _LIB
+
+
+def use_all_host_cores():
+    """Give the OpenMP loops every core this process may run on (torchrun sets OMP_NUM_THREADS=1 for its workers);
+    returns the thread count."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().ovof_set_threads(n)
+    return n
 
 
 class Vof2DCOracle:

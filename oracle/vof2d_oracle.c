@@ -127,6 +127,14 @@ int ovof2d_threads(void) {
     return 1;
 #endif
 }
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the timed CPU legs ask for the host's cores explicitly */
+void ovof_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 
 /* 2dvof.py:102-134 */
 static float find_area(const OVof *s, int i, int j, float cx, float cy, float r) {
