@@ -48,7 +48,6 @@ STEP_BYTES_3D = 236      # advect 28 + rhs 20 + Jacobi 12 
 # algorithmic bytes per cell per launch (SURVEY.md 8d / DESIGN.md): fp32 arrays read + written once
 ALGO_BYTES = {"kappa": 8, "advect": 24, "rhs": 16, "jacobi": 12, "project": 24, "fct_x": 12, "fct_y": 12, "props": 12}
 STEP_BYTES_UNBLOCKED = 8 + 24 + 16 + 12 * N_JACOBI + 24 + 24          # 216 B/cell: one HBM pass per sweep
-ADVECT_RHS_FUSED_BYTES = 28                                           # R u,v,F,kappa; W u*,v*,rhs
 
 
 def workload_config(n, ic, dim=2):
@@ -277,8 +276,6 @@ def run_ours(args):
             per = tot_ms / nspan
             sweeps = (N_JACOBI * sampled_steps / nspan) if name == "jacobi" else 1.0
             bytes_cell = ALGO_BYTES[name]
-            if name == "advect" and "rhs" not in prof:
-                bytes_cell = ADVECT_RHS_FUSED_BYTES          # the predictor also writes the Poisson rhs
             algo = bytes_cell * cells_per_gpu * sweeps
             kern[name] = {"launches_per_step": nspan / sampled_steps, "ms_per_launch": per, "algo_bytes_per_cell": bytes_cell,
                           "algo_GBps": algo / (per * 1e-3) / 1e9, "share_of_step": (tot_ms / sampled_steps) / ms_step}

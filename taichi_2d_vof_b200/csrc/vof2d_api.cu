@@ -82,7 +82,6 @@ struct VofCtx {
     int opt_advect_cols;       // columns per lane of the momentum predictor (2 or 4)
     int resident[16];          // resident blocks (whole device) of the persistent streaming kernels, by variant; 0 = not asked yet
     int opt_jac_rows;          // > 0: rows per item of the blocked Jacobi (default: max(16 T, 48))
-    int opt_fit_rounds;        // 1: item sizes of the queue kernels are fitted to whole rounds of the resident warps (measured: no gain; default 0)
     int opt_chunk_cap;         // > 0: upper bound on the rows one warp marches in the streaming kernels (load-balance experiments)
     int opt_adaptive;          // 1: interface-adaptive kernels (warp-uniform bulk rows short-cut, cp.async ring), 0: first generation
     P2PEndpoint p2p;           // neighbour arenas mapped into this process (lower / upper), NVLink P2P
@@ -252,7 +251,6 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     c->opt_advect_cols = 2;
     c->opt_adaptive = 1;
     c->opt_chunk_cap = 0;
-    c->opt_fit_rounds = 0;
     c->sm_count = prop.multiProcessorCount;
     c->all_a = std::max(0, -g.gi0);
     c->all_b = std::min(g.nrows - 1, P.nx + 1 - g.gi0);
@@ -405,20 +403,6 @@ static void launch_queue(VofCtx* c, K kern, int slot, int warps_per_block, int n
     kern<<<blocks, 32 * warps_per_block, 0, c->stream>>>(args...);
 }
 
-// Experiment (VOF_OPT_FIT_ROUNDS, off by default): persistent warps take their items in rounds and 4.6 rounds might cost 5
-// (ncu: SMs active 81-88 % of the queue kernels), so shrink the items a little until their number fills whole rounds of
-// the resident warps.  Measured at 8192^2: advect 0.404 -> 0.395 ms, the blocked Jacobi 0.374 -> 0.400 (more redundant
-// rows), the others unchanged -- the idle share is not round quantisation.
-static int fit_rounds(const VofCtx* c, int rows, int nstrips, int rpc, int resident_warps, int min_rows) {
-    if (!c->opt_fit_rounds) return rpc;
-    const long long nitems = (long long)nstrips * cdiv(rows, rpc);
-    if (nitems <= resident_warps) return rpc;                               // one round or less: nothing to fit
-    const long long m = (nitems + resident_warps - 1) / resident_warps;     // rounds these items need anyway
-    const long long nchunks = m * resident_warps / nstrips;                 // chunks that fill m rounds
-    if (nchunks <= 0) return rpc;
-    return std::min(rpc, std::max(min_rows, cdiv(rows, (int)nchunks)));
-}
-
 static unsigned bc_mask_all = 31u;
 
 static int run_set_bc(VofCtx* c, unsigned mask) {
@@ -447,7 +431,6 @@ static int run_kappa(VofCtx* c) {
     // adaptive kernel: items come from a queue and bulk rows are nearly free, so short items (less tail behind the
     // few expensive interface items) cost little; first generation: long chunks amortise the 4 warm-up rows
     int rpc = c->opt_adaptive ? chunk_rows(c, rows, nstrips, 6, 24) : chunk_rows(c, rows, nstrips, 6, 64);
-    if (c->opt_adaptive) rpc = fit_rounds(c, rows, nstrips, rpc, resident_blocks(c, k_kappa5, 32 * kKapWarps, 4) * kKapWarps, 6);
     dim3 grid(cdiv(nstrips * cdiv(rows, rpc), kKapWarps));
     if (c->opt_adaptive) {
         const int nitems = nstrips * cdiv(rows, rpc);
@@ -463,8 +446,7 @@ static int run_advect(VofCtx* c, bool inline_props) {
     const int rows = b - a + 1;
     const int nc = c->opt_advect_cols;
     const int nstrips = cdiv(c->g.ny, 32 * nc);
-    int rpc = chunk_rows(c, rows, nstrips, 4, 64);
-    if (c->opt_adaptive && inline_props && nc == 2) rpc = fit_rounds(c, rows, nstrips, rpc, resident_blocks(c, k_advect5<2>, 32 * kMomWarps, 7) * kMomWarps, 4);
+    const int rpc = chunk_rows(c, rows, nstrips, 4, 64);
     dim3 grid(cdiv(nstrips * cdiv(rows, rpc), kMomWarps));
     if (c->opt_adaptive && inline_props && nc == 2) {
         const int nitems = nstrips * cdiv(rows, rpc);
@@ -535,7 +517,6 @@ static int launch_jacobi_tb(VofCtx* c, const float* pin, float* pout) {
         const long long want_items = 2LL * c->jac_resident_warps[T];
         const int fill = (int)std::min<long long>(rpc_max, (long long)rows * sc.nstrips / want_items);
         sc.rpc = std::min(rows, std::max(rpc_min, fill));
-        sc.rpc = fit_rounds(c, rows, sc.nstrips, sc.rpc, c->jac_resident_warps[T], rpc_min);
     }
     sc.nchunks = cdiv(rows, sc.rpc);
     sc.counter = &c->diag->queue;
@@ -617,13 +598,6 @@ static int run_fct_x(VofCtx* c, bool post) {
     const int nstrips = cdiv(c->g.ny + 1, 32 * nc);
     int rpc = c->opt_adaptive ? chunk_rows(c, rows, nstrips, 6, 48)             // queue-scheduled: shorter items, less tail
                               : chunk_rows(c, rows, nstrips, 6, 96);            // 6 warm-up rows are re-read per chunk
-    if (c->opt_adaptive) {
-        const int res = nc == 2 ? (post ? resident_blocks(c, k_fct_x5<true, 2, FctOps2, false>, 32 * kFctXWarps, 0)
-                                        : resident_blocks(c, k_fct_x5<false, 2, FctOps2, false>, 32 * kFctXWarps, 1))
-                                : (post ? resident_blocks(c, k_fct_x5<true, 4, FctOps2, false>, 32 * kFctXWarps, 2)
-                                        : resident_blocks(c, k_fct_x5<false, 4, FctOps2, false>, 32 * kFctXWarps, 3));
-        rpc = fit_rounds(c, rows, nstrips, rpc, res * kFctXWarps, 6);
-    }
     const int nwarps = nstrips * cdiv(rows, rpc);
     dim3 grid(cdiv(nwarps, kFctXWarps));
 #define FXA c->g, c->fctx, c->F(), c->buf[BUF_U], c->F_alt(), c->in_a, c->in_b, rpc, nstrips
@@ -655,11 +629,6 @@ static int run_fct_y(VofCtx* c, bool post) {
     const int rows = c->all_b - c->all_a + 1;
     const int nstrips = cdiv(c->g.ny + 1, kFctYValid);
     int rpw = chunk_rows(c, rows, nstrips, 2, 16);
-    if (c->opt_adaptive) {
-        const int res = post ? resident_blocks(c, k_fct_y5<true, FctOps2, false>, 32 * kFctYWarps, 5)
-                             : resident_blocks(c, k_fct_y5<false, FctOps2, false>, 32 * kFctYWarps, 6);
-        rpw = fit_rounds(c, rows, nstrips, rpw, res * kFctYWarps, 2);
-    }
     const int nwarps = nstrips * cdiv(rows, rpw);
     dim3 grid(cdiv(nwarps, kFctYWarps));
 #define FYA c->g, c->fcty, c->F(), c->buf[BUF_V], c->F_alt(), c->all_a, c->all_b, rpw, nstrips
@@ -1106,7 +1075,6 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
         case VOF_OPT_ADVECT_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "advect columns per lane must be 2 or 4"); c->opt_advect_cols = value; break;
         case VOF_OPT_JACOBI_MAXT: if (value < 0 || value > 5) return fail(VOF_EINVAL, "jacobi sweeps per pass must be 0 (by grid size) or 1..5"); c->opt_jacobi_maxt = value; break;
         case VOF_OPT_JACOBI_ROWS: if (value < 0) return fail(VOF_EINVAL, "jacobi rows per item must be >= 0"); c->opt_jac_rows = value; break;
-        case VOF_OPT_FIT_ROUNDS: if (value != 0 && value != 1) return fail(VOF_EINVAL, "fit_rounds must be 0 or 1"); c->opt_fit_rounds = value; break;
         case VOF_OPT_CHUNK_CAP: if (value < 0) return fail(VOF_EINVAL, "chunk cap must be >= 0"); c->opt_chunk_cap = value; break;
         case VOF_OPT_ADAPTIVE: if (value != 0 && value != 1) return fail(VOF_EINVAL, "adaptive must be 0 or 1"); c->opt_adaptive = value; break;
         case VOF_OPT_FCT_X_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "fct_x columns per lane must be 2 or 4"); c->opt_fct_x_cols = value; break;

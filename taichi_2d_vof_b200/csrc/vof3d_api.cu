@@ -34,7 +34,6 @@ struct Vof3Ctx {
     long long launches;
     int sm_count, resident[8];  // resident blocks (whole device) of the queue-scheduled kernels, by variant
     int opt_jac_rows;          // planes one block of k3_jacobi5 marches
-    int opt_jac_smem;          // 1: k3_jacobi6 (j-neighbours through shared memory: measured 10 % slower), 0 (default): k3_jacobi5
     bool bc_clean;             // every ghost cell is what set_BC would write now (true after a whole step; any other writer clears it)
     int opt_gen2;              // 1 (default): second-generation kernels, 0: first generation (same bits)
     P2PEndpoint p2p;           // neighbour arenas (lower / upper) mapped for the NVLink peer-store halo exchange
@@ -102,7 +101,6 @@ extern "C" int vof3d_create(const VofParams* in, Vof3Ctx** out) {
     memset(c, 0, sizeof(*c));
     c->opt_gen2 = 1;
     c->opt_jac_rows = kJacRows3;
-    c->opt_jac_smem = 0;
     c->device = dev; c->g = g;
     c->lo = P.slab_lo; c->hi = P.slab_hi; c->H = P.halo;
     c->has_lo = c->lo == 1; c->has_hi = c->hi == P.nx;
@@ -263,8 +261,7 @@ static int run3_jacobi(Vof3Ctx* c, int mode) {
         if (c->opt_gen2) {
             const int rows = std::max(1, std::min(c->opt_jac_rows, planes));
             dim3 g5(cdiv(c->g.nz, 128), cdiv(c->g.ny + 2, 4), cdiv(planes, rows));
-            if (c->opt_jac_smem) k3_jacobi6<<<g5, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, rows);
-            else k3_jacobi5<<<g5, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, rows);
+            k3_jacobi5<<<g5, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, rows);
         } else {
             dim3 g4(cdiv(c->g.nz + 1, 128), cdiv(c->g.ny + 2, 4), cdiv(planes, kRows3));
             k3_jacobi4<<<g4, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, kRows3);
@@ -613,11 +610,6 @@ extern "C" int vof3d_p2p_check(Vof3Ctx* c) {
 
 extern "C" int vof3d_set_option(Vof3Ctx* c, int option, int value) {
     if (!c) return fail(VOF_EINVAL, "null context");
-    if (option == VOF_OPT_JACOBI_TB) {      // 3-D: 1 = lines of a block exchange their plane through shared memory (default 0)
-        if (value != 0 && value != 1) return fail(VOF_EINVAL, "3-D jacobi_tb must be 0 or 1");
-        c->opt_jac_smem = value;
-        return VOF_OK;
-    }
     if (option == VOF_OPT_CHUNK_CAP) {
         if (value < 0) return fail(VOF_EINVAL, "chunk cap must be >= 0");
         c->opt_jac_rows = value > 0 ? value : kJacRows3;

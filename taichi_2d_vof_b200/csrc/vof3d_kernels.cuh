@@ -563,123 +563,6 @@ k3_jacobi5(Grid3 g, Consts3 c, Jac3C jc, const float* __restrict__ p, float* __r
     }
 }
 
-// ---- 7-point sweep, third generation: as k3_jacobi5, but the four lines of a block hand each other their plane through
-// shared memory (double-buffered, one barrier per plane) instead of re-reading p[i, j-1, k] and p[i, j+1, k] through
-// L1 / L2: per plane step a block issues 4 + 2 + 4 global float4 loads per lane instead of 16.  Measured 10 % SLOWER than
-// k3_jacobi5 at 512^3 (4.72 vs 4.28 ms per 10 sweeps): the barrier per plane costs more than the L2 traffic it saves.
-// Kept behind vof3d_set_option(VOF_OPT_JACOBI_TB, 1) as a documented negative result.
-__global__ void __launch_bounds__(128)
-k3_jacobi6(Grid3 g, Consts3 c, Jac3C jc, const float* __restrict__ p, float* __restrict__ pn, const float* __restrict__ rhs,
-           int r0, int r1, int rows_per_block) {
-    __shared__ float4 sp[2][6][32];       // planes i (mod 2) x lines j0-1 .. j0+4 of the block x lanes
-    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-    const int j0 = blockIdx.y * 4, j = j0 + wl;
-    const int kl = 1 + (blockIdx.x * 32 + lane) * 4;                      // == 1 (mod 4): 16-byte aligned
-    const bool line = j <= g.ny + 1;                                      // warps past the last line only keep the barriers
-    const bool active = line && kl <= g.nz;
-    const int ia = r0 + blockIdx.z * rows_per_block, ib = min(r1, ia + rows_per_block - 1);
-    if (ia > ib) return;
-    const size_t si = (size_t)g.pj, sj = (size_t)g.pk;
-    size_t o = (size_t)ia * si + (size_t)j * sj + kl;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int last = g.nrows - 1;
-    const bool jin = j >= 1 && j <= g.ny;
-    const bool jw = j == 1 || j == g.ny;
-    const float an = (j != g.ny) ? c.dyi2 : 0.0f, as = (j != 1) ? c.dyi2 : 0.0f;
-    bool kin[4], kw[4];
-    float af[4], ab[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int k = kl + q;
-        kin[q] = k <= g.nz; kw[q] = k == 1 || k == g.nz;
-        af[q] = (k != g.nz) ? c.dzi2 : 0.0f; ab[q] = (k != 1) ? c.dzi2 : 0.0f;
-    }
-    const bool strip_kwall = __any_sync(0xffffffffu, active && (kw[0] || kw[1] || kw[2] || kw[3]));
-    const bool left_edge = active && lane == 0;                           // reads column kl-1 itself
-    const bool left_ghost = active && kl == 1;                            // ... and copies it (ghost column 0)
-    const bool right_edge = active && (lane == 31 || kl + 4 == g.nz + 1); // reads column kl+4 itself
-    const bool right_ghost = active && kl + 4 == g.nz + 1;                // ... and copies it (ghost column nz+1)
-    auto ldc = [&](const float* b, size_t q, bool ok) { return ok ? *reinterpret_cast<const float4*>(b + q) : z4; };
-    // row i: centre planes i-1, i, i+1, the j-neighbours and rhs of plane i, the two k-edge values
-    float4 p_m = (active && ia > 0) ? ldc(p, o - si, true) : z4;
-    float4 p_c = ldc(p, o, active);
-    float4 p_p = ldc(p, o + si, active && ia + 1 <= last);
-    float4 b_c = ldc(rhs, o, active && jin);
-    // the block's lines exchange their plane through shared memory; the two lines next to the block come from global memory
-    const bool halo_lo = wl == 0 && j0 >= 1 && kl <= g.nz, halo_hi = wl == 3 && j0 + 4 <= g.ny + 1 && kl <= g.nz;
-    const size_t oh = halo_lo ? o - sj : o + sj;                          // (plane ia) offset of this warp's halo line
-    const bool halo = halo_lo || halo_hi;
-    float4 h_p = ldc(p, oh + si, halo && ia + 1 <= last);
-    sp[ia & 1][wl + 1][lane] = p_c;
-    if (halo) sp[ia & 1][halo_lo ? 0 : 5][lane] = ldc(p, oh, true);
-    __syncthreads();
-    float le_c = left_edge ? p[o - 1] : 0.0f, re_c = right_edge ? p[o + 4] : 0.0f;
-    for (int i = ia; i <= ib; ++i, o += si) {
-        const int gi = g.gi0 + i;
-        // requests for row i+1
-        const bool more = i + 1 <= ib;
-        const size_t on = o + si;
-        const float4 p_pp = ldc(p, on + si, active && more && i + 2 <= last);
-        const float4 h_pp = ldc(p, oh + (size_t)(i - ia + 2) * si, halo && more && i + 2 <= last);
-        const float4 jm_c = active ? sp[i & 1][wl][lane] : z4, jp_c = active ? sp[i & 1][wl + 2][lane] : z4;
-        const float4 b_n = ldc(rhs, on, active && more && jin);
-        const float le_n = (left_edge && more) ? p[on - 1] : 0.0f, re_n = (right_edge && more) ? p[on + 4] : 0.0f;
-
-        float left = __shfl_up_sync(0xffffffffu, p_c.w, 1), right = __shfl_down_sync(0xffffffffu, p_c.x, 1);
-        if (left_edge) left = le_c;
-        if (right_edge) right = re_c;
-        float4 out = p_c;
-        const bool rowin = gi >= 1 && gi <= g.nx;
-        if (rowin && jin) {                                               // warp-uniform
-            const bool iw = gi == 1 || gi == g.nx;
-            const float ae = (gi != g.nx) ? c.dxi2 : 0.0f, aw = (gi != 1) ? c.dxi2 : 0.0f;
-            const float pc[4] = {p_c.x, p_c.y, p_c.z, p_c.w}, pp[4] = {p_p.x, p_p.y, p_p.z, p_p.w}, pm[4] = {p_m.x, p_m.y, p_m.z, p_m.w};
-            const float jp[4] = {jp_c.x, jp_c.y, jp_c.z, jp_c.w}, jm[4] = {jm_c.x, jm_c.y, jm_c.z, jm_c.w}, bb[4] = {b_c.x, b_c.y, b_c.z, b_c.w};
-            float t[4], r[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float kp = q < 3 ? pc[q + 1] : right, km = q > 0 ? pc[q - 1] : left;
-                t[q] = bb[q] - ae * pp[q];
-                t[q] = t[q] - aw * pm[q];
-                t[q] = t[q] - an * jp[q];
-                t[q] = t[q] - as * jm[q];
-                t[q] = t[q] - af[q] * kp;
-                t[q] = t[q] - ab[q] * km;
-            }
-            if (jc.fast_div_ok && !iw && !jw) {
-                bool slow = false;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { r[q] = div_by_const_core(t[q], jc.dv.b, jc.dv.r); slow = slow || div_needs_ieee(t[q]); }
-                if (__any_sync(0xffffffffu, slow)) {                      // sub-normal quotients: the fp64 scheme
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) if (div_needs_ieee(t[q])) r[q] = div_slow(t[q], jc.dv);
-                }
-                if (strip_kwall) {                                        // warp-uniform: first and last strip only
-                    const float ap1 = c.ap[0][0][1];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) if (kw[q]) r[q] = div_nz(t[q], ap1);   // k-wall cells: another diagonal
-                }
-            } else {
-                const float ap0 = c.ap[iw ? 1 : 0][jw ? 1 : 0][0], ap1 = c.ap[iw ? 1 : 0][jw ? 1 : 0][1];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) r[q] = div_nz(t[q], kw[q] ? ap1 : ap0);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) r[q] = kin[q] ? r[q] : pc[q];      // ghost / pad columns pass through
-            out = make_float4(r[0], r[1], r[2], r[3]);
-        }
-        if (active) *reinterpret_cast<float4*>(pn + o) = out;
-        if (left_ghost) pn[o - 1] = le_c;                                 // ghost column k = 0 passes through
-        if (right_ghost) pn[o + 4] = re_c;                                // ghost column k = nz+1 (when it starts a float4)
-        // plane i+1 of this line (and of the halo line) for the neighbours' next step
-        sp[(i + 1) & 1][wl + 1][lane] = p_p;
-        if (halo) sp[(i + 1) & 1][halo_lo ? 0 : 5][lane] = h_p;
-        __syncthreads();
-        p_m = p_c; p_c = p_p; p_p = p_pp; h_p = h_pp; b_c = b_n; le_c = le_n; re_c = re_n;
-    }
-}
-
-
 // ---- update_uv (3dvof.py:286-302) -----------------------------------------------------------------------------------
 template <bool INLINE_PROPS>
 __global__ void __launch_bounds__(kB3)

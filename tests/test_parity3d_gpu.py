@@ -142,28 +142,6 @@ def test_lean_bc_tracks_outside_writers_3d(built_lib):
         _same(s, o, CORE, f"lean-bc step {step}")
 
 
-def test_jacobi_smem_exchange_identical_3d(built_lib):
-    """k3_jacobi6 (lines of a block exchange their plane through shared memory) against k3_jacobi5, random pressure incl.
-    ghosts, sizes that leave partial blocks (ny + 2 not a multiple of 4) and partial strips."""
-    from taichi_2d_vof_b200 import VofSolver3D, _lib, reference_params3d
-    rng = np.random.default_rng(21)
-    for (nx, ny, nz) in ((9, 13, 130), (12, 8, 128), (7, 5, 21)):
-        shp = (nx + 2, ny + 2, nz + 2)
-        p0 = ((rng.random(shp, dtype=np.float32) - 0.5) * 50).astype(np.float32)
-        us = ((rng.random(shp, dtype=np.float32) - 0.5) * 1e-3).astype(np.float32)
-        F0 = rng.random(shp, dtype=np.float32)
-        out = []
-        for smem in (1, 0):
-            s = VofSolver3D(reference_params3d(nx=nx, ny=ny, nz=nz, Lx=0.1 * nx / 200, Ly=0.1 * ny / 200, Lz=0.1 * nz / 200))
-            s.set_option(_lib.VOF_OPT_JACOBI_TB, smem)
-            s.p.from_numpy(p0); s.F.from_numpy(F0)
-            for k in ("u_star", "v_star", "w_star"):
-                getattr(s, k).from_numpy(us)
-            s.cal_nu_rho(); s.solve_p_jacobi(7)
-            out.append(s.p.to_numpy())
-        assert out[0].tobytes() == out[1].tobytes(), f"{(nx, ny, nz)}: p differs between k3_jacobi6 and k3_jacobi5"
-
-
 import glob as _glob
 import os as _os
 
