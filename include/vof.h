@@ -183,6 +183,11 @@ enum {
     VOF_OPT_JACOBI_MAXT = 5,  /* sweeps per HBM pass of the blocked Jacobi at most: 0 (default) by grid size (3 up to ~5800^2,
                                  5 beyond), or 1 .. 5 */
     VOF_OPT_JACOBI_ROWS = 7,  /* > 0: rows per work item of the blocked Jacobi (tuning; default 0 = max(16 T, 48)) */
+    VOF_OPT_JACOBI_LONG_PCT = 8, /* third-generation Jacobi: percent of the rows cut into one long work item per resident warp (default 75;
+                                  the rest becomes short items of VOF_OPT_JACOBI_ROWS rows, default max(8 T, 24)) */
+    VOF_OPT_JACOBI_PK = 6,    /* 1 (default): blocked Jacobi of the third generation (Blackwell packed fp32x2 arithmetic, c*p products,
+                               * cp.async rings; vof2d_jacobi_pk.cuh;
+                               * square cells only), 0: second generation; same bits */
     VOF_OPT_CHUNK_CAP = 4,    /* > 0: cap on the rows one warp marches per work item in the streaming kernels (tuning) */
     VOF_OPT_ADAPTIVE = 3      /* 1 (default): interface-adaptive FCT / curvature kernels -- bulk rows where F is uniform
                                  across a warp's strip take an exact short-cut, the x-sweep streams rows through a

@@ -24,7 +24,9 @@ VOF_OPT_ADVECT_COLS = 2
 VOF_OPT_ADAPTIVE = 3
 VOF_OPT_CHUNK_CAP = 4
 VOF_OPT_JACOBI_MAXT = 5
+VOF_OPT_JACOBI_PK = 6
 VOF_OPT_JACOBI_ROWS = 7
+VOF_OPT_JACOBI_LONG_PCT = 8
 VOF_VIEW_VOF, VOF_VIEW_U, VOF_VIEW_V, VOF_VIEW_VNORM = 0, 1, 2, 3
 VOF_STEP_MATERIALIZE_PROPS = 1
 VOF_STEP_NO_FUSION = 2

@@ -6,6 +6,7 @@
 #include "vof_host_common.h"
 #include "vof2d_kernels.cuh"
 #include "vof2d_jacobi_tb.cuh"
+#include "vof2d_jacobi_pk.cuh"
 #include "vof2d_fct.cuh"
 #include "vof2d_momentum.cuh"
 #include "vof2d_kappa.cuh"
@@ -76,6 +77,9 @@ struct VofCtx {
     MomC mom;                  // constants of the momentum predictor
     JacTB jac;                 // constants of the temporally blocked Jacobi
     int jac_resident_warps[6]; // warps of k_jacobi_tb<T> resident on the whole GPU, by T
+    int jac_resident_warps_pk[6];
+    int opt_jac_long_pct;      // third-generation Jacobi: share of the rows (percent) cut into one long item per resident warp
+    int opt_jacobi_pk;         // 1 (default): third-generation blocked Jacobi (packed fp32x2, vof2d_jacobi_pk.cuh), 0: second generation
     int opt_jacobi_tb;         // 1: temporal blocking (default), 0: one launch per sweep
     int opt_jacobi_maxt;       // sweeps per HBM pass at most: 0 = by grid size, else 1..5 (5: 10 sweeps = 5 + 5; 3: 3 + 3 + 2 + 2)
     int opt_fct_x_cols;        // columns per lane of the x-sweep (2 or 4)
@@ -246,6 +250,8 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     }
     c->mom.k = k; c->mom.d_dx = make_const_div(k.dx); c->mom.d_dy = make_const_div(k.dy); c->mom.fast_div_ok = 0;
     c->opt_jacobi_tb = 1;
+    c->opt_jacobi_pk = 1;
+    c->opt_jac_long_pct = 75;
     c->opt_jacobi_maxt = 0;
     c->opt_fct_x_cols = 2;
     c->opt_advect_cols = 2;
@@ -498,9 +504,58 @@ static int run_jacobi_sweep(VofCtx* c, int rhs_mode) {
     return launch_ok("k_jacobi");
 }
 
+// Third generation (packed fp32x2 arithmetic, c*p products, cp.async rings; vof2d_jacobi_pk.cuh)
+template <int T>
+static int launch_jacobi_pk(VofCtx* c, const float* pin, float* pout) {
+    auto kern_pk = k_jacobi_pk<T>;
+    if (!c->jac_resident_warps_pk[T]) {
+        int nb = 0;
+        CU(cudaFuncSetAttribute(kern_pk, cudaFuncAttributeMaxDynamicSharedMemorySize, kPkSmem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern_pk, 32 * kPkWarps, kPkSmem));
+        c->jac_resident_warps_pk[T] = std::max(1, nb) * kPkWarps * c->sm_count;
+    }
+    const int resident = c->jac_resident_warps_pk[T];
+    const int ra = c->in_a, rb = c->in_b, rows = rb - ra + 1;
+    PkSched sc;
+    sc.nstrips = cdiv(c->g.ny, JacStrip<T>::valid);
+    sc.right_first = sc.nstrips;
+    for (int st = 1; st < sc.nstrips; ++st) {
+        const int jstrip = 1 - JacStrip<T>::margin + st * JacStrip<T>::valid;
+        if (!(jstrip >= 2 && jstrip + kJacStripCols - 1 <= c->g.ny - 1)) { sc.right_first = st; break; }
+    }
+    // Interior strips: the 2T + 1 rows next to an i-wall are items of their own (general variant); between them one
+    // long item per resident warp over the first `long_pct` of the rows and short items over the rest -- a grid too
+    // small for that (long items of fewer than two short ones) gets short items only.  Edge strips: short items.
+    {
+        const int short_rows = c->opt_jac_rows > 0 ? c->opt_jac_rows : std::max(8 * T, 24);
+        sc.wlo = c->has_lo ? std::min(rows / 2, 2 * T + 1) : 0;
+        sc.whi = c->has_hi ? std::min(rows / 2, 2 * T + 1) : 0;
+        const int mid = rows - sc.wlo - sc.whi;
+        const int wps = std::max(1, resident / sc.nstrips);                 // resident warps per strip
+        const int rowsA = (int)((long long)mid * c->opt_jac_long_pct / 100);
+        sc.rpcA = cdiv(rowsA, wps);
+        if (sc.rpcA < 2 * short_rows) { sc.nA = 0; sc.rpcA = 0; }
+        else sc.nA = rowsA / sc.rpcA;
+        const int rest = mid - sc.nA * sc.rpcA;
+        sc.rpcB = std::min(std::max(rest, 1), short_rows);
+        sc.nB = cdiv(rest, sc.rpcB);
+        sc.rpcE = std::min(rows, std::max(short_rows, sc.rpcA / 3));
+        sc.nE = cdiv(rows, sc.rpcE);
+    }
+    sc.counter = &c->diag->queue;
+    const int nES = 1 + sc.nstrips - sc.right_first, nI = sc.nstrips - nES;
+    const int nitems = nES * sc.nE + nI * ((sc.wlo > 0) + (sc.whi > 0) + sc.nA + sc.nB);
+    CU(cudaMemsetAsync(sc.counter, 0, sizeof(unsigned int), c->stream));
+    const int nwarps = std::min(nitems, resident);
+    kern_pk<<<cdiv(nwarps, kPkWarps), 32 * kPkWarps, kPkSmem, c->stream>>>(c->g, c->jac, sc, pin, pout, c->buf[BUF_RHS], ra, rb);
+    return launch_ok("k_jacobi_pk");
+}
+
 template <int T>
 static int launch_jacobi_tb(VofCtx* c, const float* pin, float* pout) {
     const int rows = c->in_b - c->in_a + 1;
+    // third generation when the cells are square, the reciprocal division is proven exact and the slab is tall enough
+    if (c->opt_jacobi_pk && c->jac.fast_div_ok && c->jac.cx == c->jac.cy && rows >= 8 * T) return launch_jacobi_pk<T>(c, pin, pout);
     auto kern = c->jac.fast_div_ok ? k_jacobi_tb<T, true> : k_jacobi_tb<T, false>;
     if (!c->jac_resident_warps[T]) {
         int nb = 0;
@@ -510,7 +565,7 @@ static int launch_jacobi_tb(VofCtx* c, const float* pin, float* pout) {
     JacSched sc;
     sc.nstrips = cdiv(c->g.ny, JacStrip<T>::valid);
     // items small enough that the queue balances data-dependent costs (several items per resident warp),
-    // large enough that the 2T warm-up rows of an item stay a small fraction; on grids too small to fill the
+    // large enough to amortise the 2T warm-up rows of a chunk (16T rows: 11 % redundant); on grids that cannot fill the
     // device that way the items shrink (down to 4T rows: 1.5x the work, but every SM has some)
     {
         const int rpc_max = c->opt_jac_rows > 0 ? c->opt_jac_rows : std::max(16 * T, 48), rpc_min = 4 * T;
@@ -544,13 +599,23 @@ static int jacobi_max_sweeps(const VofCtx* c) {
     return jacobi_field_mb(c) > 400.0 ? 5 : 3;
 }
 
-// nsweeps sweeps from the hoisted rhs, at most 5 per HBM pass; `frame`: keep ghost cells of p exact
-static int run_jacobi_tb(VofCtx* c, int nsweeps, bool frame) {
+// nsweeps sweeps from the hoisted rhs, at most 5 per HBM pass.  The blocked kernels store interior cells only and ghost
+// cells pass through a sweep unchanged (2dvof.py:265-266 copies the interior): one copy of the frame into the other
+// ping-pong buffer before the first pass keeps the ghosts of both buffers equal to the reference's single array for
+// every pass (they enter the sweeps as 0 * p[ghost], whose sign is the ghost's).
+static int run_jacobi_tb(VofCtx* c, int nsweeps) {
     const int npass = cdiv(nsweeps, jacobi_max_sweeps(c));
     const int base = nsweeps / npass, extra = nsweeps % npass;
     for (int k = 0; k < npass; ++k) {
         const int T = base + (k < extra ? 1 : 0);
-        Span span_(c, VOF_K_JACOBI, frame ? 2 : 1);
+        Span span_(c, VOF_K_JACOBI, k == 0 ? 2 : 1);
+        if (k == 0) {
+            const int nrow = c->all_b - c->all_a + 1;
+            const int lo_row = c->has_lo ? 0 - c->g.gi0 : -1, hi_row = c->has_hi ? c->g.nx + 1 - c->g.gi0 : -1;
+            const int n = nrow + (lo_row >= 0 ? c->g.ny + 2 : 0) + (hi_row >= 0 ? c->g.ny + 2 : 0);
+            k_copy_frame<<<cdiv(n, 128), 128, 0, c->stream>>>(c->g, c->p(), c->p_alt(), c->all_a, c->all_b, lo_row, hi_row);
+            TRY(launch_ok("k_copy_frame"));
+        }
         int rc = VOF_OK;
         switch (T) {
             case 1: rc = launch_jacobi_tb<1>(c, c->p(), c->p_alt()); break;
@@ -560,13 +625,6 @@ static int run_jacobi_tb(VofCtx* c, int nsweeps, bool frame) {
             default: rc = launch_jacobi_tb<5>(c, c->p(), c->p_alt()); break;
         }
         if (rc != VOF_OK) return rc;
-        if (frame) {
-            const int nrow = c->all_b - c->all_a + 1;
-            const int lo_row = c->has_lo ? 0 - c->g.gi0 : -1, hi_row = c->has_hi ? c->g.nx + 1 - c->g.gi0 : -1;
-            const int n = nrow + (lo_row >= 0 ? c->g.ny + 2 : 0) + (hi_row >= 0 ? c->g.ny + 2 : 0);
-            k_copy_frame<<<cdiv(n, 128), 128, 0, c->stream>>>(c->g, c->p(), c->p_alt(), c->all_a, c->all_b, lo_row, hi_row);
-            TRY(launch_ok("k_copy_frame"));
-        }
         c->p_cur ^= 1;
     }
     return VOF_OK;
@@ -677,7 +735,7 @@ extern "C" int vof2d_solve_p_jacobi(VofCtx* c, int nsweeps) {
     if (nsweeps == 1) return run_jacobi_sweep(c, 1);   // the reference's structure: rhs recomputed inside the sweep
     if (nsweeps == 0) return VOF_OK;
     TRY(run_rhs(c, false));
-    if (use_jacobi_tb(c)) return run_jacobi_tb(c, nsweeps, true);
+    if (use_jacobi_tb(c)) return run_jacobi_tb(c, nsweeps);
     for (int s = 0; s < nsweeps; ++s) TRY(run_jacobi_sweep(c, 0));
     return VOF_OK;
 }
@@ -789,7 +847,7 @@ static int step_impl(VofCtx* c, int istep, unsigned flags) {
     TRY(run_advect(c, true));
     TRY(run_set_bc(c, mask));
     TRY(run_rhs(c, true));
-    if (use_jacobi_tb(c) && c->P.n_jacobi > 0) TRY(run_jacobi_tb(c, c->P.n_jacobi, false));
+    if (use_jacobi_tb(c) && c->P.n_jacobi > 0) TRY(run_jacobi_tb(c, c->P.n_jacobi));
     else for (int s = 0; s < c->P.n_jacobi; ++s) TRY(run_jacobi_sweep(c, 0));
     TRY(run_project(c, true));
     TRY(run_set_bc(c, mask));
@@ -1077,6 +1135,8 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
         case VOF_OPT_JACOBI_ROWS: if (value < 0) return fail(VOF_EINVAL, "jacobi rows per item must be >= 0"); c->opt_jac_rows = value; break;
         case VOF_OPT_CHUNK_CAP: if (value < 0) return fail(VOF_EINVAL, "chunk cap must be >= 0"); c->opt_chunk_cap = value; break;
         case VOF_OPT_ADAPTIVE: if (value != 0 && value != 1) return fail(VOF_EINVAL, "adaptive must be 0 or 1"); c->opt_adaptive = value; break;
+        case VOF_OPT_JACOBI_LONG_PCT: if (value < 0 || value > 100) return fail(VOF_EINVAL, "jacobi long-item share must be 0 .. 100"); c->opt_jac_long_pct = value; break;
+        case VOF_OPT_JACOBI_PK: if (value != 0 && value != 1) return fail(VOF_EINVAL, "jacobi_pk must be 0 or 1"); c->opt_jacobi_pk = value; break;
         case VOF_OPT_FCT_X_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "fct_x columns per lane must be 2 or 4"); c->opt_fct_x_cols = value; break;
         default: return fail(VOF_EINVAL, "unknown option %d", option);
     }

@@ -207,12 +207,14 @@ def test_diagnostics_and_torch_view(built_lib):
     assert d["residual"] >= 0
 
 
+@pytest.mark.parametrize("pk", [1, 0])
 @pytest.mark.parametrize("maxt", [5, 4])
 @pytest.mark.parametrize("nsweeps", [1, 2, 3, 4, 5, 6, 7, 10, 11])
-@pytest.mark.parametrize("shape", [(70, 300), (400, 130)])
-def test_jacobi_temporal_blocking_equals_single_sweeps(built_lib, nsweeps, shape, maxt):
-    """vof2d_solve_p_jacobi(n) (<= 5 sweeps per HBM pass, register-pipelined) must equal n calls of the
-    reference's single sweep exactly -- interior, walls (zeroed coefficients) and the untouched ghost frame."""
+@pytest.mark.parametrize("shape", [(70, 300), (400, 130), (97, 131)])
+def test_jacobi_temporal_blocking_equals_single_sweeps(built_lib, nsweeps, shape, maxt, pk):
+    """vof2d_solve_p_jacobi(n) (<= 5 sweeps per HBM pass, register-pipelined; pk = 1: the packed fp32x2 kernel of the
+    third generation, 0: the second) must equal n calls of the reference's single sweep exactly -- interior, walls
+    (zeroed coefficients) and the untouched ghost frame (random, both signs: it enters as 0 * p[ghost])."""
     rng = np.random.default_rng(nsweeps)
     nx, ny = shape
     P = Vof2DParams(nx=nx, ny=ny, Lx=0.1 * nx / 200, Ly=0.1 * ny / 200)
@@ -228,6 +230,9 @@ def test_jacobi_temporal_blocking_equals_single_sweeps(built_lib, nsweeps, shape
     s = _solver(P)
     s.set_option(_lib.VOF_OPT_JACOBI_TB, 2)      # force the blocked kernel (small grids default to single sweeps)
     s.set_option(_lib.VOF_OPT_JACOBI_MAXT, maxt)  # 5: 10 = 5 + 5 sweeps per pass; 4: 4 + 3 + 3, narrower strip margins
+    s.set_option(_lib.VOF_OPT_JACOBI_PK, pk)
+    o.p[1, 1:4] = [3e-37, -2e-38, 1e-44]          # tiny numerators in a wall row / corner, subnormal included
+    o.p[nx, ny - 2:ny + 1] = [-1e-40, 2e-39, -3e-36]
     for k in ("rho", "u_star", "v_star", "p"):
         getattr(s, k).from_numpy(getattr(o, k))
     for _ in range(nsweeps):
@@ -236,6 +241,33 @@ def test_jacobi_temporal_blocking_equals_single_sweeps(built_lib, nsweeps, shape
     a, b = s.p.to_numpy(), o.p
     bad = np.argwhere(a != b)
     assert bad.size == 0, f"{len(bad)} cells differ, first {bad[0]}: {a[tuple(bad[0])]} vs {b[tuple(bad[0])]}"
+
+
+@pytest.mark.parametrize("long_pct,rows", [(75, 0), (0, 17), (100, 24), (50, 9)])
+def test_packed_jacobi_item_sizes_identical(built_lib, long_pct, rows):
+    """The packed kernel's work items (edge strips, wall rows, long and short chunks of the bulk) tile the grid for
+    every item size: 1700 x 520 (5 strips, two of them edge strips), 10 sweeps, against the second generation."""
+    from taichi_2d_vof_b200 import _lib
+    rng = np.random.default_rng(7)
+    P = Vof2DParams(nx=1700, ny=520, Lx=0.85, Ly=0.26)
+    outs = []
+    for pk in (0, 1):
+        s = _solver(P)
+        s.set_option(_lib.VOF_OPT_JACOBI_TB, 2)
+        s.set_option(_lib.VOF_OPT_JACOBI_PK, pk)
+        if pk:
+            s.set_option(_lib.VOF_OPT_JACOBI_LONG_PCT, long_pct)
+            s.set_option(_lib.VOF_OPT_JACOBI_ROWS, rows)
+        shp = (P.nx + 2, P.ny + 2)
+        rng2 = np.random.default_rng(11)
+        s.rho.from_numpy(50 + 950 * rng2.random(shp, dtype=np.float32))
+        s.u_star.from_numpy((rng2.random(shp, dtype=np.float32) - 0.5) * 1e-3)
+        s.v_star.from_numpy((rng2.random(shp, dtype=np.float32) - 0.5) * 1e-3)
+        s.p.from_numpy((rng2.random(shp, dtype=np.float32) - 0.5) * 100.0)
+        s.solve_p_jacobi(10)
+        outs.append(s.p.to_numpy())
+    bad = np.argwhere(outs[0] != outs[1])
+    assert bad.size == 0, f"{len(bad)} cells differ, first {bad[0]}"
 
 
 def test_jacobi_tb_on_off_identical(built_lib):
