@@ -109,6 +109,11 @@ int vof2d_fct_x_sweep(VofCtx* c);               /* 2dvof.py:321-382             
 int vof2d_fct_y_sweep(VofCtx* c);               /* 2dvof.py:385-448                           */
 int vof2d_solve_VOF_rudman(VofCtx* c, int istep);/* 2dvof.py:312-318                          */
 int vof2d_post_process_f(VofCtx* c);            /* 2dvof.py:452-455                           */
+/* The stand-alone FCT variant of test/forward_fct.py: solve_VOF_rudman(t, eps_value) :254-264 = fct_y_sweep :310-351 and
+ * fct_x_sweep :267-308 in the order of the step's parity, set_BC(F) :218-229 after each; F advected by the u, v fields as they
+ * are (the script's init_uv / set_init_F are the caller's: field_set).  eps regularises the limiter ratios (:286, :293);
+ * no var() clamp.  Full-domain contexts.  Bit-identical to the script run (tests/golden/ref_fct_*.npz). */
+int vof2d_fct_forward(VofCtx* c, int istep, float eps);
 
 /* ---- the loop body 2dvof.py:513-528 as one call (fused kernels, same result) ---- */
 int vof2d_step(VofCtx* c, int istep, unsigned flags);
@@ -185,6 +190,9 @@ enum {
     VOF_OPT_JACOBI_ROWS = 7,  /* > 0: rows per work item of the blocked Jacobi (tuning; default 0 = max(16 T, 48)) */
     VOF_OPT_JACOBI_LONG_PCT = 8, /* third-generation Jacobi: percent of the rows cut into one long work item per resident warp (default 75;
                                   the rest becomes short items of VOF_OPT_JACOBI_ROWS rows, default max(8 T, 24)) */
+    VOF_OPT_PRESSURE_SOLVER = 9, /* 0 (default): the reference's Jacobi sweeps (2dvof.py:236-266, 521-522); 1: the same number of
+                                  sweeps of the Chebyshev semi-iterative acceleration of that iteration -- a stronger
+                                  projection for the same traffic per sweep.  Changes p, u, v: outside parity mode */
     VOF_OPT_JACOBI_PK = 6,    /* 1 (default): blocked Jacobi of the third generation (Blackwell packed fp32x2 arithmetic, c*p products,
                                * cp.async rings; vof2d_jacobi_pk.cuh;
                                * square cells only), 0: second generation; same bits */

@@ -27,6 +27,7 @@ VOF_OPT_JACOBI_MAXT = 5
 VOF_OPT_JACOBI_PK = 6
 VOF_OPT_JACOBI_ROWS = 7
 VOF_OPT_JACOBI_LONG_PCT = 8
+VOF_OPT_PRESSURE_SOLVER = 9
 VOF_VIEW_VOF, VOF_VIEW_U, VOF_VIEW_V, VOF_VIEW_VNORM = 0, 1, 2, 3
 VOF_STEP_MATERIALIZE_PROPS = 1
 VOF_STEP_NO_FUSION = 2
@@ -91,6 +92,7 @@ SIGNATURES = {
     "vof2d_fct_y_sweep": (C.c_int, [_ctx]),
     "vof2d_solve_VOF_rudman": (C.c_int, [_ctx, C.c_int]),
     "vof2d_post_process_f": (C.c_int, [_ctx]),
+    "vof2d_fct_forward": (C.c_int, [_ctx, C.c_int, C.c_float]),
     "vof2d_display_field": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
     "vof2d_display_field_dev": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
     "vof2d_interp_velocity": (C.c_int, [_ctx, C.c_void_p]),

@@ -10,6 +10,7 @@
 #include "vof2d_fct.cuh"
 #include "vof2d_momentum.cuh"
 #include "vof2d_kappa.cuh"
+#include "vof2d_extras.cuh"
 #include "vof_p2p.cuh"
 
 using namespace vof;
@@ -79,6 +80,7 @@ struct VofCtx {
     int jac_resident_warps[6]; // warps of k_jacobi_tb<T> resident on the whole GPU, by T
     int jac_resident_warps_pk[6];
     int opt_jac_long_pct;      // third-generation Jacobi: share of the rows (percent) cut into one long item per resident warp
+    int opt_pressure_solver;   // 0 (default): the reference's Jacobi sweeps; 1: Chebyshev-accelerated Jacobi (changes p: outside parity mode)
     int opt_jacobi_pk;         // 1 (default): third-generation blocked Jacobi (packed fp32x2, vof2d_jacobi_pk.cuh), 0: second generation
     int opt_jacobi_tb;         // 1: temporal blocking (default), 0: one launch per sweep
     int opt_jacobi_maxt;       // sweeps per HBM pass at most: 0 = by grid size, else 1..5 (5: 10 sweeps = 5 + 5; 3: 3 + 3 + 2 + 2)
@@ -630,6 +632,47 @@ static int run_jacobi_tb(VofCtx* c, int nsweeps) {
     return VOF_OK;
 }
 
+// Opt-in stronger pressure solver: nsweeps iterations of the Chebyshev semi-iterative
+// method on the reference's Jacobi iteration, from the hoisted rhs.  rho = (1 + cos(pi / max(nx, ny))) / 2 bounds the
+// spectrum of the Jacobi matrix on the Neumann grid away from the constant mode (which the iteration leaves alone:
+// the polynomial is 1 at eigenvalue 1); w(1) = 1, w(2) = 1 / (1 - rho^2 / 2), w(k+1) = 1 / (1 - rho^2 w(k) / 4).
+static int run_jacobi_cheb(VofCtx* c, int nsweeps) {
+    const double rho = 0.5 * (1.0 + std::cos(M_PI / std::max(c->g.nx, c->g.ny)));
+    double w = 1.0;
+    for (int k = 1; k <= nsweeps; ++k) {
+        if (k == 1) { TRY(run_jacobi_sweep(c, 0)); continue; }      // x(1) = J x(0); also makes the other buffer's frame current
+        w = k == 2 ? 1.0 / (1.0 - 0.5 * rho * rho) : 1.0 / (1.0 - 0.25 * rho * rho * w);
+        Span span_(c, VOF_K_JACOBI);
+        const int rows = c->all_b - c->all_a + 1;
+        const int rpb = chunk_rows(c, rows, cdiv(c->g.ny + 2, 32), 4, 32);
+        dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, rpb));
+        k_jacobi_cheb<<<grid, kBlockJ, 0, c->stream>>>(c->g, c->k, c->p(), c->p_alt(), c->buf[BUF_RHS], (float)w, c->all_a, c->all_b, rpb);
+        TRY(launch_ok("k_jacobi_cheb"));
+        c->p_cur ^= 1;
+    }
+    return VOF_OK;
+}
+
+// test/forward_fct.py:254-264: solve_VOF_rudman(t, eps) of the stand-alone FCT variant, set_BC(F) after each sweep
+static int run_fct_forward(VofCtx* c, int istep, float eps) {
+    if (c->g.gi0 != 0 || c->g.nrows != c->g.nx + 2) return fail(VOF_ESTATE, "the forward-FCT variant needs a full-domain context");
+    FwdC fx{c->k.dt, c->k.dx, c->k.dy, c->k.dxdy, c->k.dtdy, eps}, fy = fx;
+    fy.dtd = c->k.dtdx;
+    const dim3 grid(cdiv(c->g.ny, 128), c->g.nx);
+    for (int half = 0; half < 2; ++half) {
+        const bool y = (istep % 2 == 0) == (half == 0);
+        ++c->launches;
+        if (y) k_fct_forward<1><<<grid, 128, 0, c->stream>>>(c->g, fy, c->F(), c->buf[BUF_V], c->F_alt());
+        else k_fct_forward<0><<<grid, 128, 0, c->stream>>>(c->g, fx, c->F(), c->buf[BUF_U], c->F_alt());
+        TRY(launch_ok("k_fct_forward"));
+        // ghost cells of the new level start from the old level's (the reference's F[level + 1] starts from zeros and
+        // set_BC then writes every ghost cell: same result)
+        c->F_cur ^= 1;
+        TRY(run_set_bc(c, 4u));
+    }
+    return VOF_OK;
+}
+
 static int run_project(VofCtx* c, bool inline_props) {
     Span span_(c, VOF_K_PROJECT);
     const int a = std::max(c->in_a, 1), b = c->in_b;
@@ -735,10 +778,12 @@ extern "C" int vof2d_solve_p_jacobi(VofCtx* c, int nsweeps) {
     if (nsweeps == 1) return run_jacobi_sweep(c, 1);   // the reference's structure: rhs recomputed inside the sweep
     if (nsweeps == 0) return VOF_OK;
     TRY(run_rhs(c, false));
+    if (c->opt_pressure_solver == 1) return run_jacobi_cheb(c, nsweeps);
     if (use_jacobi_tb(c)) return run_jacobi_tb(c, nsweeps);
     for (int s = 0; s < nsweeps; ++s) TRY(run_jacobi_sweep(c, 0));
     return VOF_OK;
 }
+extern "C" int vof2d_fct_forward(VofCtx* c, int istep, float eps) { CHECK_CTX(c); return run_fct_forward(c, istep, eps); }
 extern "C" int vof2d_update_uv(VofCtx* c) { CHECK_CTX(c); return run_project(c, false); }
 extern "C" int vof2d_fct_x_sweep(VofCtx* c) { CHECK_CTX(c); return run_fct_x(c, false); }
 extern "C" int vof2d_fct_y_sweep(VofCtx* c) { CHECK_CTX(c); return run_fct_y(c, false); }
@@ -847,7 +892,8 @@ static int step_impl(VofCtx* c, int istep, unsigned flags) {
     TRY(run_advect(c, true));
     TRY(run_set_bc(c, mask));
     TRY(run_rhs(c, true));
-    if (use_jacobi_tb(c) && c->P.n_jacobi > 0) TRY(run_jacobi_tb(c, c->P.n_jacobi));
+    if (c->opt_pressure_solver == 1 && c->P.n_jacobi > 0) TRY(run_jacobi_cheb(c, c->P.n_jacobi));
+    else if (use_jacobi_tb(c) && c->P.n_jacobi > 0) TRY(run_jacobi_tb(c, c->P.n_jacobi));
     else for (int s = 0; s < c->P.n_jacobi; ++s) TRY(run_jacobi_sweep(c, 0));
     TRY(run_project(c, true));
     TRY(run_set_bc(c, mask));
@@ -1136,6 +1182,7 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
         case VOF_OPT_CHUNK_CAP: if (value < 0) return fail(VOF_EINVAL, "chunk cap must be >= 0"); c->opt_chunk_cap = value; break;
         case VOF_OPT_ADAPTIVE: if (value != 0 && value != 1) return fail(VOF_EINVAL, "adaptive must be 0 or 1"); c->opt_adaptive = value; break;
         case VOF_OPT_JACOBI_LONG_PCT: if (value < 0 || value > 100) return fail(VOF_EINVAL, "jacobi long-item share must be 0 .. 100"); c->opt_jac_long_pct = value; break;
+        case VOF_OPT_PRESSURE_SOLVER: if (value != 0 && value != 1) return fail(VOF_EINVAL, "pressure solver must be 0 (Jacobi) or 1 (Chebyshev)"); c->opt_pressure_solver = value; break;
         case VOF_OPT_JACOBI_PK: if (value != 0 && value != 1) return fail(VOF_EINVAL, "jacobi_pk must be 0 or 1"); c->opt_jacobi_pk = value; break;
         case VOF_OPT_FCT_X_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "fct_x columns per lane must be 2 or 4"); c->opt_fct_x_cols = value; break;
         default: return fail(VOF_EINVAL, "unknown option %d", option);

@@ -33,6 +33,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument('--scaled', action='store_true', help="constant-dx scaling: L = 0.1 * nx / 200")
     p.add_argument('--dt', type=float, default=4e-6)
     p.add_argument('--jacobi', type=int, default=10)
+    p.add_argument('--pressure-solver', choices=['jacobi', 'chebyshev'], default='jacobi',
+                   help="'chebyshev': the same number of sweeps of the Chebyshev-accelerated Jacobi iteration (stronger projection; "
+                        "not the reference's arithmetic)")
     p.add_argument('--steps', type=int, default=0, help="stop after this many steps (0 = run until interrupted, like the GUI loop)")
     p.add_argument('--nstep', type=int, default=100, help="output interval (2dvof.py:497)")
     p.add_argument('--sequence', action='store_true', help="call one C-ABI entry per reference kernel instead of the fused vof2d_step")
@@ -99,6 +102,10 @@ def main(argv=None) -> int:
 
     slab = SlabSolver2D(params_fn, nx, rank, world, dist=dist, n_jacobi=args.jacobi, device=device, transport=args.transport)
     s = slab.solver
+    if args.pressure_solver == 'chebyshev':
+        from . import _lib
+        s.set_option(_lib.VOF_OPT_PRESSURE_SOLVER, 1)
+        say('>>> Pressure solver: Chebyshev-accelerated Jacobi (opt-in; results differ from the reference)')
     nstep = args.nstep                      # 2dvof.py:497
     if args.resume:
         st = np.load(args.resume)

@@ -193,6 +193,14 @@ class VofSolver2D:
     def solve_VOF_rudman(self):
         check(self._L.vof2d_solve_VOF_rudman(self._h, int(self.istep)))
 
+    def fct_forward(self, eps: float = 1.0e-4, istep: int | None = None):
+        """``solve_VOF_rudman(t, eps_value)`` of the reference's test/forward_fct.py:254-264 (the stand-alone FCT
+        variant) for step ``t`` (default: the solver's step counter, which it advances)."""
+        t = self.istep if istep is None else int(istep)
+        check(self._L.vof2d_fct_forward(self._h, t, float(eps)))
+        if istep is None:
+            self.istep += 1
+
     def post_process_f(self):
         check(self._L.vof2d_post_process_f(self._h))
 

@@ -158,3 +158,30 @@ def test_fixture_is_what_the_reference_text_computes_today():
                 for k in old.files:
                     if old[k].dtype == np.float32:
                         refpin.assert_same(new[k], old[k], f"{name} {k} (max/min ties: {mode})")
+
+
+@pytest.mark.parametrize("name", refpin.fixtures("fct_"))
+def test_forward_fct_oracle_equals_reference_run(name):
+    """The stand-alone FCT variant (test/forward_fct.py:254-351, Kothe-Rider vortex): every stored half-step level of
+    the reference run, from its level 0 and its u, v, against oracle/fct_forward_oracle.py -- bit for bit."""
+    from oracle.fct_forward_oracle import FctForwardOracle
+    z, meta = refpin.load(name)
+    n = refpin.sizes(meta)
+    o = FctForwardOracle(n["nx"], n["ny"], meta["dx"], meta["dy"], meta["dt"], meta["eps"])
+    levels = [int(v) for v in z["levels"]]
+    o.F[...] = z["F_levels"][levels.index(0)]
+    o.u[...] = z["u"]
+    o.v[...] = z["v"]
+    want = dict(zip(levels, z["F_levels"]))
+    checked = 0
+    for t in range(n["tmax"]):
+        order = (1, 0) if t % 2 == 0 else (0, 1)
+        for half, axis in enumerate(order):
+            o._sweep(axis)
+            o.set_BC()
+            lvl = 2 * t + half + 1
+            if lvl in want:
+                refpin.assert_same(o.F, want[lvl], f"{name} level {lvl}")
+                checked += 1
+        o.t += 1
+    assert checked == len(levels) - 1

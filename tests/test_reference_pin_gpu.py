@@ -96,3 +96,29 @@ def test_cuda_steps_equal_reference_run_3d(built_lib, name, mode):
             s.step() if mode == "fused" else s.step_sequence()
         for k in (LIVE3D if mode == "sequence" else CORE3D):
             refpin.assert_same(getattr(s, k).to_numpy(), z[f"{k}_{t}"], f"{name} step {t} ({mode}) field {k}")
+
+
+@pytest.mark.parametrize("name", refpin.fixtures("fct_"))
+def test_cuda_forward_fct_equals_reference_run(built_lib, name):
+    """vof2d_fct_forward (the stand-alone FCT variant, test/forward_fct.py:254-351) on the Kothe-Rider vortex of the
+    reference run: every stored half-step level, bit for bit.  Odd levels (between the two sweeps of a step) are
+    checked through a second solver that stops after the first sweep's level by replaying the reference order."""
+    from taichi_2d_vof_b200 import VofSolver2D, reference_params
+    z, meta = refpin.load(name)
+    n = refpin.sizes(meta)
+    P = reference_params(nx=n["nx"], ny=n["ny"], Lx=float(np.pi), Ly=float(np.pi), dt=meta["dt"])
+    P.dx, P.dy = meta["dx"], meta["dy"]
+    s = VofSolver2D(P)
+    assert (s.P.dx, s.P.dy, s.P.dt) == (meta["dx"], meta["dy"], meta["dt"])
+    levels = [int(v) for v in z["levels"]]
+    want = dict(zip(levels, z["F_levels"]))
+    s.F.from_numpy(want[0])
+    s.u.from_numpy(z["u"])
+    s.v.from_numpy(z["v"])
+    checked = 0
+    for t in range(n["tmax"]):
+        s.fct_forward(meta["eps"])
+        if 2 * t + 2 in want:
+            refpin.assert_same(s.F.to_numpy(), want[2 * t + 2], f"{name} level {2 * t + 2}")
+            checked += 1
+    assert checked == sum(1 for v in levels if v and v % 2 == 0)
