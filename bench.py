@@ -497,7 +497,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--dim", type=int, choices=[2, 3], default=2, help="3: the 3dvof.py path (BASELINE config 5), a fixed n^3 grid over the GPUs")
-    ap.add_argument("--n", type=int, default=0, help="cells per side per GPU (default: the metric's 8192; 512 with --dim 3)")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=0, help="cells per side per GPU (default: the metric's 8192; 512 with --dim 3)")
     ap.add_argument("--nx-global", type=int, default=0, help="fixed global rows (strong scaling) instead of --n rows per GPU")
     ap.add_argument("--ny", type=int, default=0, help="columns with --nx-global (default: square)")
     ap.add_argument("--ic", type=int, choices=[1, 2, 3], default=3)
