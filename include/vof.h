@@ -193,6 +193,8 @@ enum {
     VOF_OPT_PRESSURE_SOLVER = 9, /* 0 (default): the reference's Jacobi sweeps (2dvof.py:236-266, 521-522); 1: the same number of
                                   sweeps of the Chebyshev semi-iterative acceleration of that iteration -- a stronger
                                   projection for the same traffic per sweep.  Changes p, u, v: outside parity mode */
+    VOF_OPT_PACKED = 10,      /* 1 (default): Blackwell packed fp32x2 arithmetic (FFMA2) in the streaming kernels that have a packed
+                                  variant (momentum predictor); 0: scalar arithmetic; same bits */
     VOF_OPT_JACOBI_PK = 6,    /* 1 (default): blocked Jacobi of the third generation (Blackwell packed fp32x2 arithmetic, c*p products,
                                * cp.async rings; vof2d_jacobi_pk.cuh;
                                * square cells only), 0: second generation; same bits */

@@ -81,6 +81,7 @@ struct VofCtx {
     int jac_resident_warps_pk[6];
     int opt_jac_long_pct;      // third-generation Jacobi: share of the rows (percent) cut into one long item per resident warp
     int opt_pressure_solver;   // 0 (default): the reference's Jacobi sweeps; 1: Chebyshev-accelerated Jacobi (changes p: outside parity mode)
+    int opt_packed;            // 1 (default): packed fp32x2 arithmetic in the streaming kernels that have it (same bits)
     int opt_jacobi_pk;         // 1 (default): third-generation blocked Jacobi (packed fp32x2, vof2d_jacobi_pk.cuh), 0: second generation
     int opt_jacobi_tb;         // 1: temporal blocking (default), 0: one launch per sweep
     int opt_jacobi_maxt;       // sweeps per HBM pass at most: 0 = by grid size, else 1..5 (5: 10 sweeps = 5 + 5; 3: 3 + 3 + 2 + 2)
@@ -219,6 +220,7 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     k.rho_l = (float)P.rho_l; k.rho_g = (float)P.rho_g; k.nu_l = (float)P.nu_l; k.nu_g = (float)P.nu_g;
     k.gx = (float)P.gx; k.gy = (float)P.gy;
     k.cflx = (float)(0.25 * dx); k.cfly = (float)(0.25 * dy);
+    k.one = 1.0f; k.neg_zero = -0.0f;
     // initial-condition constants (2dvof.py:141-158)
     InitConsts ic{};
     ic.hdx = (float)(dx / 2); ic.hdy = (float)(dy / 2); ic.sqrt2dx = (float)(std::sqrt(2.0) * dx);
@@ -253,6 +255,7 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     c->mom.k = k; c->mom.d_dx = make_const_div(k.dx); c->mom.d_dy = make_const_div(k.dy); c->mom.fast_div_ok = 0;
     c->opt_jacobi_tb = 1;
     c->opt_jacobi_pk = 1;
+    c->opt_packed = 1;
     c->opt_jac_long_pct = 75;
     c->opt_jacobi_maxt = 0;
     c->opt_fct_x_cols = 2;
@@ -454,13 +457,16 @@ static int run_advect(VofCtx* c, bool inline_props) {
     const int rows = b - a + 1;
     const int nc = c->opt_advect_cols;
     const int nstrips = cdiv(c->g.ny, 32 * nc);
-    const int rpc = chunk_rows(c, rows, nstrips, 4, 64);
+    // queue items of at most 24 rows: an item costs two warm-up rows only, and with 64-row items the SMs idled 15 % of
+    // the kernel behind the last items (ncu: sm__cycles_active min / max 652k / 849k; 8192^2: 0.458 -> 0.403 ms)
+    const int rpc = chunk_rows(c, rows, nstrips, 4, (c->opt_adaptive && inline_props && nc == 2) ? 24 : 64);
     dim3 grid(cdiv(nstrips * cdiv(rows, rpc), kMomWarps));
     if (c->opt_adaptive && inline_props && nc == 2) {
         const int nitems = nstrips * cdiv(rows, rpc);
         WorkQueue wq{c->diag->wq, nitems};
 #define ADQ c->g, c->mom, wq, c->buf[BUF_U], c->buf[BUF_V], c->F(), c->buf[BUF_KAPPA], c->buf[BUF_US], c->buf[BUF_VS], a, b, rpc, nstrips
-        launch_queue(c, k_advect5<2>, 7, kMomWarps, nitems, ADQ);      // 4 columns per lane would need > 48 KB of ring
+        if (c->opt_packed) launch_queue(c, k_advect5<2, true>, 8, kMomWarps, nitems, ADQ);    // packed fp32x2 arithmetic (FFMA2)
+        else launch_queue(c, k_advect5<2, false>, 7, kMomWarps, nitems, ADQ);     // 4 columns per lane would need > 48 KB of ring
 #undef ADQ
         return launch_ok("k_advect5");
     }
@@ -1183,6 +1189,7 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
         case VOF_OPT_ADAPTIVE: if (value != 0 && value != 1) return fail(VOF_EINVAL, "adaptive must be 0 or 1"); c->opt_adaptive = value; break;
         case VOF_OPT_JACOBI_LONG_PCT: if (value < 0 || value > 100) return fail(VOF_EINVAL, "jacobi long-item share must be 0 .. 100"); c->opt_jac_long_pct = value; break;
         case VOF_OPT_PRESSURE_SOLVER: if (value != 0 && value != 1) return fail(VOF_EINVAL, "pressure solver must be 0 (Jacobi) or 1 (Chebyshev)"); c->opt_pressure_solver = value; break;
+        case VOF_OPT_PACKED: if (value != 0 && value != 1) return fail(VOF_EINVAL, "packed must be 0 or 1"); c->opt_packed = value; break;
         case VOF_OPT_JACOBI_PK: if (value != 0 && value != 1) return fail(VOF_EINVAL, "jacobi_pk must be 0 or 1"); c->opt_jacobi_pk = value; break;
         case VOF_OPT_FCT_X_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "fct_x columns per lane must be 2 or 4"); c->opt_fct_x_cols = value; break;
         default: return fail(VOF_EINVAL, "unknown option %d", option);

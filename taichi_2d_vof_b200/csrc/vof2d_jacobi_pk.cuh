@@ -28,20 +28,6 @@
 
 namespace vof {
 
-typedef unsigned long long f32x2;      // two fp32 in an aligned register pair: .x = low half = the lower column
-
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-
 struct PkConsts {
     f32x2 c, r, nb, m1, nz;     // (c, c), (1/ap, 1/ap), (-ap, -ap), (-1, -1), (-0, -0)
 };

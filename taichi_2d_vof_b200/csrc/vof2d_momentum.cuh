@@ -150,6 +150,131 @@ __device__ __forceinline__ void adv_row(const AdvState<INLINE_PROPS, NC>& S, con
     }
 }
 
+// --------------------------------------------------------------------------------------
+// adv_row for two columns per lane in Blackwell packed fp32 (FFMA2, vof_common.cuh): the lane's two cells are the two
+// halves of every operand, each packed operation is one separately rounded operation of the reference in both halves,
+// in the reference's order (2dvof.py:208-233).  Selects (upwind direction) and the CSF term -- non-zero only where F
+// jumps across the face -- stay per element.  Half the arithmetic issue slots of adv_row<true, 2, PH>, same bits.
+// --------------------------------------------------------------------------------------
+struct AdvPkC {
+    f32x2 dxi, dyi, dxi2, dyi2, gx, gy, dt, quarter, two;
+    Pk2 o;
+};
+__device__ __forceinline__ AdvPkC adv_pk_consts(const Consts& k) {
+    AdvPkC c;
+    c.dxi = pk2(k.dxi); c.dyi = pk2(k.dyi); c.dxi2 = pk2(k.dxi2); c.dyi2 = pk2(k.dyi2);
+    c.gx = pk2(k.gx); c.gy = pk2(k.gy); c.dt = pk2(k.dt); c.quarter = pk2(0.25f); c.two = pk2(2.0f);
+    c.o = pk2_ops(k);
+    return c;
+}
+__device__ __forceinline__ f32x2 sel2(float c0, float c1, f32x2 pos, f32x2 neg) {      // (c > 0 ? pos : neg) per half
+    float p0, p1, n0, n1;
+    unpk2(pos, p0, p1);
+    unpk2(neg, n0, n1);
+    return pk2(c0 > 0.0f ? p0 : n0, c1 > 0.0f ? p1 : n1);
+}
+
+template <int PH>
+__device__ __forceinline__ void adv_row_pk(const AdvState<true, 2>& S, const MomC& c, const AdvPkC& K, int P,
+                                           float* __restrict__ us, float* __restrict__ vs, size_t off, int gi, int jl, int nx,
+                                           int ny) {
+    constexpr int P1 = PH, C = (PH + 2) % 3, M = (PH + 1) % 3;   // rows i+1, i, i-1
+    const Consts& k = c.k;
+    const float* uC = S.u[C].x; const float* uM = S.u[M].x; const float* uP = S.u[P1].x;
+    const float* vC = S.v[C].x; const float* vM = S.v[M].x; const float* vP = S.v[P1].x;
+    const f32x2 u_c = pk2(uC[1], uC[2]), u_m = pk2(uM[1], uM[2]), u_p = pk2(uP[1], uP[2]);
+    const f32x2 u_jm = pk2(uC[0], uC[1]), u_jp = pk2(uC[2], uC[3]);
+    const f32x2 v_c = pk2(vC[1], vC[2]), v_m = pk2(vM[1], vM[2]), v_p = pk2(vP[1], vP[2]);
+    const f32x2 v_jm = pk2(vC[0], vC[1]), v_jp = pk2(vC[2], vC[3]);
+    const f32x2 nu_c = pk2(S.nu[C][0], S.nu[C][1]);
+    const f32x2 F_c = pk2(S.F[C].x[1], S.F[C].x[2]);
+    float ou[2], ov[2];
+    {   // ---- u*  (2dvof.py:208-220)
+        f32x2 v_here = K.o.add(v_m, pk2(vM[2], vM[3]));
+        v_here = K.o.add(v_here, v_c);
+        v_here = K.o.mul(K.quarter, K.o.add(v_here, v_jp));
+        const f32x2 dudx = sel2(uC[1], uC[2], K.o.mul(K.o.sub(u_c, u_m), K.dxi), K.o.mul(K.o.sub(u_p, u_c), K.dxi));
+        float vh0, vh1;
+        unpk2(v_here, vh0, vh1);
+        const f32x2 dudy = sel2(vh0, vh1, K.o.mul(K.o.sub(u_c, u_jm), K.dyi), K.o.mul(K.o.sub(u_jp, u_c), K.dyi));
+        const f32x2 two_u = K.o.mul(K.two, u_c);
+        f32x2 acc = K.o.mul(K.o.mul(nu_c, K.o.add(K.o.sub(u_m, two_u), u_p)), K.dxi2);
+        acc = K.o.add(acc, K.o.mul(K.o.mul(nu_c, K.o.add(K.o.sub(u_jm, two_u), u_jp)), K.dyi2));
+        acc = K.o.sub(acc, K.o.mul(u_c, dudx));
+        acc = K.o.sub(acc, K.o.mul(v_here, dudy));
+        acc = K.o.add(acc, K.gx);
+        const f32x2 dF = K.o.sub(F_c, pk2(S.F[M].x[1], S.F[M].x[2]));
+        float d0, d1;
+        unpk2(dF, d0, d1);
+        if (d0 != 0.0f || d1 != 0.0f) {           // otherwise the CSF term is +-0 in both cells
+            float a[2];
+            unpk2(acc, a[0], a[1]);
+            const float d[2] = {d0, d1};
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (d[q] != 0.0f) {
+                    const int e = q + 1;
+                    const float kappa_ave = (S.kp[C].x[e] + S.kp[M].x[e]) / 2.0f;
+                    const float t = (k.neg_sigma * d[q]) * kappa_ave;
+                    const float fx_kappa = c.fast_div_ok ? div_by_const(t, c.d_dx) : t / k.dx;
+                    a[q] = a[q] + (fx_kappa * 2.0f) / (rho_of(S.F[C].x[e], k) + rho_of(S.F[M].x[e], k));
+                }
+            acc = pk2(a[0], a[1]);
+        }
+        unpk2(K.o.add(u_c, K.o.mul(K.dt, acc)), ou[0], ou[1]);
+    }
+    {   // ---- v*  (2dvof.py:221-233)
+        f32x2 u_here = K.o.add(u_jm, u_c);
+        u_here = K.o.add(u_here, pk2(uP[0], uP[1]));
+        u_here = K.o.mul(K.quarter, K.o.add(u_here, u_p));
+        float uh0, uh1;
+        unpk2(u_here, uh0, uh1);
+        const f32x2 dvdx = sel2(uh0, uh1, K.o.mul(K.o.sub(v_c, v_m), K.dxi), K.o.mul(K.o.sub(v_p, v_c), K.dxi));
+        const f32x2 dvdy = sel2(vC[1], vC[2], K.o.mul(K.o.sub(v_c, v_jm), K.dyi), K.o.mul(K.o.sub(v_jp, v_c), K.dyi));
+        const f32x2 two_v = K.o.mul(K.two, v_c);
+        f32x2 acc = K.o.mul(K.o.mul(nu_c, K.o.add(K.o.sub(v_m, two_v), v_p)), K.dxi2);
+        acc = K.o.add(acc, K.o.mul(K.o.mul(nu_c, K.o.add(K.o.sub(v_jm, two_v), v_jp)), K.dyi2));
+        acc = K.o.sub(acc, K.o.mul(u_here, dvdx));
+        acc = K.o.sub(acc, K.o.mul(v_c, dvdy));
+        acc = K.o.add(acc, K.gy);
+        const f32x2 dF = K.o.sub(F_c, pk2(S.F[C].x[0], S.F[C].x[1]));
+        float d0, d1;
+        unpk2(dF, d0, d1);
+        if (d0 != 0.0f || d1 != 0.0f) {
+            float a[2];
+            unpk2(acc, a[0], a[1]);
+            const float d[2] = {d0, d1};
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if (d[q] != 0.0f) {
+                    const int e = q + 1;
+                    const float kappa_ave = (S.kp[C].x[e] + S.kp[C].x[e - 1]) / 2.0f;
+                    const float t = (k.neg_sigma * d[q]) * kappa_ave;
+                    const float fy_kappa = c.fast_div_ok ? div_by_const(t, c.d_dy) : t / k.dy;
+                    a[q] = a[q] + (fy_kappa * 2.0f) / (rho_of(S.F[C].x[e], k) + rho_of(S.F[C].x[e - 1], k));
+                }
+            acc = pk2(a[0], a[1]);
+        }
+        unpk2(K.o.add(v_c, K.o.mul(K.dt, acc)), ov[0], ov[1]);
+    }
+    // u*: gi in [2, nx], j in [1, ny];  v*: gi in [1, nx], j in [2, ny].  Everything else is never written.
+    const bool urow = gi >= 2 && gi <= nx, vrow = gi >= 1 && gi <= nx;
+    if (jl + 1 <= ny) {
+        if (urow) VecN<2>::st(us + off, ou);
+        if (vrow) {
+            if (jl >= 2) VecN<2>::st(vs + off, ov);
+            else vs[off + 1] = ov[1];
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int j = jl + q;
+            if (urow && j <= ny) us[off + q] = ou[q];
+            if (vrow && j >= 2 && j <= ny) vs[off + q] = ov[q];
+        }
+    }
+}
+
 template <bool INLINE_PROPS, int NC>
 __global__ void __launch_bounds__(32 * kMomWarps)
 k_advect4(Grid g, MomC c, const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ F,
@@ -202,7 +327,7 @@ __device__ __forceinline__ void adv_load_ring(AdvState<true, NC>& S, const MomC&
     for (int q = 0; q < NC; ++q) S.nu[PH][q] = nu_of(S.F[PH].x[q + 1], c.k);
 }
 
-template <int NC>
+template <int NC, bool PACKED>
 __global__ void __launch_bounds__(32 * kMomWarps)
 k_advect5(Grid g, MomC c, WorkQueue wq, const float* __restrict__ u, const float* __restrict__ v, const float* __restrict__ F,
           const float* __restrict__ kappa, float* __restrict__ us, float* __restrict__ vs, int r0, int r1, int rows_per_chunk,
@@ -213,6 +338,7 @@ k_advect5(Grid g, MomC c, WorkQueue wq, const float* __restrict__ u, const float
     const int P = g.pitch;
     Ring ring;
     ring.init(ring_mem, threadIdx.x);
+    const AdvPkC K = adv_pk_consts(c.k);
     for (;;) {
         const int item = wq_claim(wq, lane);
         if (item >= wq.nitems) break;
@@ -225,19 +351,26 @@ k_advect5(Grid g, MomC c, WorkQueue wq, const float* __restrict__ u, const float
         const float* const src[4] = {u + jl, v + jl, F + jl, kappa + jl};
         ring.start(active, ia - 1, ib + 1, g.nrows - 1, P, src);
         AdvState<true, NC> S;
+#define VOF_ADV_ROW(PH, I)                                                                                            \
+    if (active) {                                                                                                     \
+        if constexpr (NC == 2) { if (PACKED) adv_row_pk<PH>(S, c, K, P, us, vs, (size_t)(I) * P + col, g.gi0 + (I), jl, g.nx, g.ny); \
+                                 else adv_row<true, NC, PH>(S, c, nullptr, P, us, vs, (size_t)(I) * P + col, g.gi0 + (I), jl, g.nx, g.ny); } \
+        else adv_row<true, NC, PH>(S, c, nullptr, P, us, vs, (size_t)(I) * P + col, g.gi0 + (I), jl, g.nx, g.ny);     \
+    }
         // rows ia-1 and ia enter slots 1 and 2 (OLD and MID of phase 0)
         adv_load_ring<NC, 1>(S, c, ring, src);
         adv_load_ring<NC, 2>(S, c, ring, src);
         for (int i = ia; i <= ib; i += 3) {
             adv_load_ring<NC, 0>(S, c, ring, src);
-            if (active) adv_row<true, NC, 0>(S, c, nullptr, P, us, vs, (size_t)i * P + col, g.gi0 + i, jl, g.nx, g.ny);
+            VOF_ADV_ROW(0, i)
             if (i + 1 > ib) break;
             adv_load_ring<NC, 1>(S, c, ring, src);
-            if (active) adv_row<true, NC, 1>(S, c, nullptr, P, us, vs, (size_t)(i + 1) * P + col, g.gi0 + i + 1, jl, g.nx, g.ny);
+            VOF_ADV_ROW(1, i + 1)
             if (i + 2 > ib) break;
             adv_load_ring<NC, 2>(S, c, ring, src);
-            if (active) adv_row<true, NC, 2>(S, c, nullptr, P, us, vs, (size_t)(i + 2) * P + col, g.gi0 + i + 2, jl, g.nx, g.ny);
+            VOF_ADV_ROW(2, i + 2)
         }
+#undef VOF_ADV_ROW
     }
     ring.drain();
     wq_leave(wq, lane, gridDim.x * kMomWarps);

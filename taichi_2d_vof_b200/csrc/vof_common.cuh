@@ -27,6 +27,8 @@ struct Consts {
     float neg_sigma;         // -sigma[None]                  2dvof.py:213
     float rho_l, rho_g, nu_l, nu_g, gx, gy;
     float cflx, cfly;        // 0.25*dx, 0.25*dy              2dvof.py:274, 279
+    float one, neg_zero;     // 1.0f and -0.0f as RUN-TIME values: operands of the packed fp32x2 forms that ptxas must not
+                             // recognise as a plain add / multiply (it would contract the pair into one FFMA2, see Pk2)
 };
 
 // Geometry of one context's local arrays.  Local row l holds global row gi0 + l.
@@ -67,6 +69,42 @@ __device__ __forceinline__ float div_nz(float t, float b) {
     float r = t * (b < 0.0f ? -1.0f : 1.0f);
     if (t != 0.0f) { asm volatile("" ::: "memory"); r = t / b; }
     return r;
+}
+
+// ---- Blackwell packed fp32 (PTX fma.rn.f32x2, SASS FFMA2: one issue slot, two independent fp32 operations) ----------
+// Only the fma form is used, with operands that make it a single separately rounded operation of the reference:
+//   a * b = fma(a, b, -0)   the exact product plus -0 rounds once, and x + (-0) = x for every x including +-0
+//   a + b = fma(a, 1, b)    a * 1 is exact
+//   a - b = fma(b, -1, a)   b * (-1) is exact; signs of zero as in a - b
+// (ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under -fmad=false, so those forms are not used.)
+typedef unsigned long long f32x2;      // two fp32 in an aligned register pair: low half = the lower column
+
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 pk2(float both) { return pk2(both, both); }
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// With LITERAL 1 and -0 ptxas rewrites the two forms above to FADD2 / FMUL2 and then contracts an adjacent FMUL2 + FADD2
+// pair into one FFMA2 -- even under -fmad=false (seen in SASS; three cells of a 300 x 700 step differed).  The operations
+// of a kernel whose products feed sums directly therefore take 1 and -0 from kernel parameters (Consts::one, neg_zero):
+// every operation stays a genuine three-operand FFMA2, and two fmas cannot be fused.
+struct Pk2 {
+    f32x2 one, nz, m1;
+    __device__ __forceinline__ f32x2 mul(f32x2 a, f32x2 b) const { return fma2(a, b, nz); }
+    __device__ __forceinline__ f32x2 add(f32x2 a, f32x2 b) const { return fma2(a, one, b); }
+    __device__ __forceinline__ f32x2 sub(f32x2 a, f32x2 b) const { return fma2(b, m1, a); }
+};
+__device__ __forceinline__ Pk2 pk2_ops(const Consts& k) {
+    Pk2 o;
+    o.one = pk2(k.one); o.nz = pk2(k.neg_zero); o.m1 = pk2(-k.one);
+    return o;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -246,6 +246,7 @@ def slab_parity_check(dist, rank, world, device, nx=2048, ny=640, steps=6, ic=3,
     import numpy as np
     if three_d:
         from .solver3d import VofSolver3D as cls, reference_params3d
+        n = max(n, 24 * world)                 # every slab must be at least as thick as its halo (16 planes)
         L = 0.1 * n / 200
 
         def params_fn(slab, halo, device):
