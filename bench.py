@@ -189,6 +189,25 @@ def load_traffic():
         return {}
 
 
+def bind_to_gpu_numa_node(local):
+    """Multi-rank runs: keep this rank's threads (and, by first touch, its pinned host buffers) on the CPUs NVML lists
+    as local to its GPU, so that the e2e copies of 8 ranks do not all cross one socket's memory controllers.
+    Returns the number of CPUs bound to, or None when NVML gives no affinity."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -201,6 +220,7 @@ def run_ours(args):
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("launch N > 1 with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None      # pinned host buffers on the GPU's own NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -477,7 +497,7 @@ def run_ours(args):
                     "decomposition": ("row slabs along i, deep halo %d rows, 1 exchange/step (one fused peer-store kernel), transport %s"
                                       % (s.halo, slab.transport)) if world > 1 else "single GPU",
                     "l2": "inputs exceed L2 (live fp32 fields of %.0f MB each >> 126 MB); no flush needed" % (s.nrows * (ny + 2) * (nz + 2 if three_d else 1) * 4 / 1e6),
-                    "rows_processed_per_launch": s.nrows},
+                    "rows_processed_per_launch": s.nrows, "cpus_bound_per_rank": numa},
             "early_state": early,
             "roofline": roof, "kernels": kern, "kernels_general_path": general,
             "kernel_event_sampling": f"CUDA events around every kernel of every {prof_every}th step of the timed region" if prof_every > 1 else "CUDA events around every kernel of the timed region",

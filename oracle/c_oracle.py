@@ -3,7 +3,8 @@
 The C twin (oracle/vof2d_oracle.c) restates /root/reference/2dvof.py with the loop
 structure of the reference's ti.cpu backend; this wrapper gives it the same method
 names as oracle/vof2d_oracle.py so tests can run both side by side, and bench.py can
-time it as the CPU baseline ("port").  PARITY UNPINNED -- see vof2d_oracle.py header.
+time it as the CPU baseline ("port").  Pinned to the reference run like the NumPy form (vof2d_oracle.py header;
+tests/test_reference_pin_cpu.py::test_c_oracle_equals_reference_run_2d / _3d).
 """
 from __future__ import annotations
 

@@ -8,10 +8,11 @@
  * restatement that tests/ cross-check bit-for-bit against oracle/vof2d_oracle.py, and
  * (b) the "port" CPU baseline timed by bench.py (`cpu_baseline`, `--impl reference`).
  *
- * PARITY UNPINNED: the reference has no golden vectors / assertions for this path and its
- * runtime (taichi==1.4.1) cannot be installed in this image; arithmetic is pinned to the
- * source text: IEEE fp32, left-to-right, no FMA contraction (build with -ffp-contract=off),
- * Python-scalar sub-expressions folded in double and rounded once.
+ * PINNED to the reference run: tests/test_reference_pin_cpu.py::test_c_oracle_equals_reference_run_2d
+ * compares it bit for bit with tests/golden/ref_2d_*.npz -- the unmodified text of 2dvof.py executed
+ * under oracle/refshim/taichi (taichi==1.4.1 itself cannot be installed in this image).  Arithmetic:
+ * IEEE fp32, left-to-right, no FMA contraction (build with -ffp-contract=off), Python-scalar
+ * sub-expressions folded in double and rounded once.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may load this.
  */

@@ -3,11 +3,14 @@
 Order-exact fp32 NumPy restatement of the per-timestep path of the reference
 solver ``/root/reference/2dvof.py`` (lines 513-528 and every kernel they call).
 
-PARITY UNPINNED: the reference ships no golden vectors, no assertions and no
-fixtures for this path (``/root/reference/test/*.py`` are GUI demos of a
-*different* FCT variant), and its runtime (taichi==1.4.1, requirements.txt:3)
-is not installable in this image (py3.12, offline).  This file therefore pins
-the arithmetic to the *source text* of the reference, evaluated literally:
+PARITY PINNED TO THE REFERENCE'S OWN SOURCE, EXECUTED: ``oracle/run_reference.py`` runs the unmodified text of
+``/root/reference/2dvof.py`` (only the size constants substituted) under ``oracle/refshim/taichi`` -- a NumPy stand-in
+for taichi==1.4.1 (requirements.txt:3; not installable in this image: py3.12, offline) -- and commits what it computed
+as ``tests/golden/ref_2d_*.npz``; ``tests/test_reference_pin_cpu.py`` requires this oracle to equal those fixtures bit
+for bit, after every kernel call of the first steps and at the step snapshots (-ic 1/2/3 at the reference's 200 x 200,
+small non-square grids, injected synthetic states).  What stays outside the pin is the Taichi *compiler*: its
+``fast_math`` may re-associate at round-off level.  The reference itself ships no golden vectors
+or assertions for this path (``/root/reference/test/*.py`` are GUI demos).  The conventions the restatement follows:
 
 * every top-level ``for`` of a ``@ti.kernel`` is "read the old arrays, write the
   whole result" (NumPy slice assignment gives exactly Taichi's barrier

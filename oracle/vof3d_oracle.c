@@ -3,9 +3,9 @@
  * Scalar restatement of /root/reference/3dvof.py:126-302, 351-547 and the loop body 598-623, one
  * `#pragma omp parallel for` per top-level `for` of each @ti.kernel.  Cross-checked bit-for-bit
  * against oracle/vof3d_oracle.py by tests/; also the CPU baseline of the 3-D path.
- * PARITY UNPINNED (no golden vectors in the reference, taichi==1.4.1 not installable): arithmetic
- * is pinned to the source text -- IEEE fp32, left-to-right, -ffp-contract=off, Python-scalar
- * sub-expressions folded in double.  kappa is never computed in 3dvof.py (607), so it stays 0.
+ * PINNED to the reference run (tests/golden/ref_3d_*.npz = the unmodified 3dvof.py under oracle/refshim/taichi;
+ * tests/test_reference_pin_cpu.py::test_c_oracle_equals_reference_run_3d, bit for bit).  Arithmetic: IEEE fp32,
+ * left-to-right, -ffp-contract=off, Python-scalar sub-expressions folded in double.  kappa is never computed in 3dvof.py (607), so it stays 0.
  */
 #include <math.h>
 #include <stdint.h>

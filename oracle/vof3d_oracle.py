@@ -1,10 +1,11 @@
 """CPU oracle for the 3-D VOF hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 Order-exact fp32 NumPy restatement of the per-timestep path of ``/root/reference/3dvof.py``
-(loop body 606-623 and the kernels it calls: 141-302, 351-547).  Same conventions and the same
-PARITY UNPINNED caveat as oracle/vof2d_oracle.py: the reference has no golden vectors for this
-path and taichi==1.4.1 cannot be installed here, so the arithmetic is pinned to the source text
-(IEEE fp32, left to right, no FMA contraction, Python-scalar sub-expressions folded in double).
+(loop body 606-623 and the kernels it calls: 141-302, 351-547).  Same conventions as oracle/vof2d_oracle.py (IEEE
+fp32, left to right, no FMA contraction, Python-scalar sub-expressions folded in double) and the same pin: the
+unmodified text of 3dvof.py executed under ``oracle/refshim/taichi`` (``oracle/run_reference.py``) produced
+``tests/golden/ref_3d_*.npz``, and ``tests/test_reference_pin_cpu.py`` requires this oracle to equal them bit for bit
+after every kernel call and at the step snapshots.
 
 Facts of the 3-D script that differ from 2-D: curvature is never computed (get_normal_young is
 commented out, 304-332 / 607), so kappa == 0 and the CSF terms are exactly +-0; only ``-ic 1``

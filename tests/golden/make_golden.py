@@ -1,8 +1,8 @@
 """Generates the golden vectors under tests/golden/ from the NumPy oracle (oracle/vof2d_oracle.py).
 
-PARITY UNPINNED: the reference (taichi==1.4.1) cannot run in this image, and its own test/ directory
-holds no assertions or fixtures, so these vectors pin the ORACLE (an order-exact fp32 restatement of
-/root/reference/2dvof.py), not the Taichi binary.  Re-run: `python tests/golden/make_golden.py`.
+These vectors are the ORACLE's own output (regression fixtures at sizes / step counts the reference-run fixtures do not
+cover); what pins the oracle to the reference is tests/golden/ref_*.npz, written by oracle/run_reference.py from the
+reference's own source text executed under the taichi stand-in (tests/test_reference_pin_cpu.py).  Re-run: `python tests/golden/make_golden.py`.
 Files: vof2d_ic{1,2,3}_{nx}x{ny}.npz with u,v,p,F,kappa after 1, 10 and 100 steps + interior volumes.
 """
 import os

@@ -1,7 +1,7 @@
 """Generates the 3-D golden vectors under tests/golden/ from the NumPy oracle (oracle/vof3d_oracle.py).
 
-PARITY UNPINNED, as for the 2-D vectors: they pin the ORACLE (an order-exact fp32 restatement of
-/root/reference/3dvof.py), not the Taichi binary, which cannot run in this image.  Re-run:
+As for the 2-D vectors these are the ORACLE's own output (regression fixtures); the pin to the reference is
+tests/golden/ref_3d_*.npz (oracle/run_reference.py: the reference's own text under the taichi stand-in).  Re-run:
 `python tests/golden/make_golden3d.py`.  Files: vof3d_ic1_{nx}x{ny}x{nz}.npz with u,v,w,p,F after 1, 3 and 12
 steps (3 = one rotation of the x/y/z sweep order, 3dvof.py:351-363) + interior volumes.
 """
