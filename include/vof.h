@@ -174,7 +174,7 @@ int vof2d_diagnostics(VofCtx* c, double* mass, float* max_cfl, float* residual, 
  * group is bracketed by CUDA events recorded on the context's stream (not usable under graph replay). */
 enum {
     VOF_K_PROPS = 0, VOF_K_KAPPA, VOF_K_ADVECT, VOF_K_BC, VOF_K_RHS, VOF_K_JACOBI, VOF_K_PROJECT,
-    VOF_K_FCT_X, VOF_K_FCT_Y, VOF_K_POST, VOF_K_HALO, VOF_K_COUNT
+    VOF_K_FCT_X, VOF_K_FCT_Y, VOF_K_POST, VOF_K_HALO, VOF_K_TILE, VOF_K_COUNT
 };
 int64_t vof2d_launch_count(const VofCtx* c);
 int vof2d_profile(VofCtx* c, int enable);                 /* 0 off, 1 every launch, k > 1 the launches of every k-th vof2d_step; always resets the spans */
@@ -193,6 +193,10 @@ enum {
     VOF_OPT_PRESSURE_SOLVER = 9, /* 0 (default): the reference's Jacobi sweeps (2dvof.py:236-266, 521-522); 1: the same number of
                                   sweeps of the Chebyshev semi-iterative acceleration of that iteration -- a stronger
                                   projection for the same traffic per sweep.  Changes p, u, v: outside parity mode */
+    VOF_OPT_TILE = 11,        /* whole-step tile kernel for small grids (one launch per step, the step's dependency radius as a
+                                  shared-memory halo; csrc/vof2d_tile.cuh): 0 never, 1 (default) where the grid is launch
+                                  bound (its blocks are one wave: up to ~520^2 on 148 SMs), 2 whenever the tile fits; same bits.
+                                  The environment variable VOF_TILE overrides the default at vof2d_create (A/B runs, tests) */
     VOF_OPT_PACKED = 10,      /* 1 (default): Blackwell packed fp32x2 arithmetic (FFMA2) in the streaming kernels that have a packed
                                   variant (momentum predictor); 0: scalar arithmetic; same bits */
     VOF_OPT_JACOBI_PK = 6,    /* 1 (default): blocked Jacobi of the third generation (Blackwell packed fp32x2 arithmetic, c*p products,

@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 VOF_F, VOF_U, VOF_V, VOF_P, VOF_RHO, VOF_NU, VOF_KAPPA, VOF_USTAR, VOF_VSTAR, VOF_W, VOF_WSTAR = range(11)
 FIELD_IDS = {"F": VOF_F, "u": VOF_U, "v": VOF_V, "p": VOF_P, "rho": VOF_RHO, "nu": VOF_NU,
              "kappa": VOF_KAPPA, "u_star": VOF_USTAR, "v_star": VOF_VSTAR, "w": VOF_W, "w_star": VOF_WSTAR}
-KERNEL_KINDS = ("props", "kappa", "advect", "bc", "rhs", "jacobi", "project", "fct_x", "fct_y", "post", "halo")
+KERNEL_KINDS = ("props", "kappa", "advect", "bc", "rhs", "jacobi", "project", "fct_x", "fct_y", "post", "halo", "tile")
 VOF_OPT_JACOBI_TB = 0
 VOF_OPT_FCT_X_COLS = 1
 VOF_OPT_ADVECT_COLS = 2
@@ -29,6 +29,7 @@ VOF_OPT_JACOBI_ROWS = 7
 VOF_OPT_JACOBI_LONG_PCT = 8
 VOF_OPT_PRESSURE_SOLVER = 9
 VOF_OPT_PACKED = 10
+VOF_OPT_TILE = 11
 VOF_VIEW_VOF, VOF_VIEW_U, VOF_VIEW_V, VOF_VIEW_VNORM = 0, 1, 2, 3
 VOF_STEP_MATERIALIZE_PROPS = 1
 VOF_STEP_NO_FUSION = 2

@@ -11,6 +11,7 @@
 #include "vof2d_momentum.cuh"
 #include "vof2d_kappa.cuh"
 #include "vof2d_extras.cuh"
+#include "vof2d_tile.cuh"
 #include "vof_p2p.cuh"
 
 using namespace vof;
@@ -81,6 +82,8 @@ struct VofCtx {
     int jac_resident_warps_pk[6];
     int opt_jac_long_pct;      // third-generation Jacobi: share of the rows (percent) cut into one long item per resident warp
     int opt_pressure_solver;   // 0 (default): the reference's Jacobi sweeps; 1: Chebyshev-accelerated Jacobi (changes p: outside parity mode)
+    int opt_tile;              // whole-step tile kernel (vof2d_tile.cuh): 0 never, 1 by grid size (default), 2 whenever it fits
+    int tile_smem_set;
     int opt_packed;            // 1 (default): packed fp32x2 arithmetic in the streaming kernels that have it (same bits)
     int opt_jacobi_pk;         // 1 (default): third-generation blocked Jacobi (packed fp32x2, vof2d_jacobi_pk.cuh), 0: second generation
     int opt_jacobi_tb;         // 1: temporal blocking (default), 0: one launch per sweep
@@ -256,6 +259,8 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     c->opt_jacobi_tb = 1;
     c->opt_jacobi_pk = 1;
     c->opt_packed = 1;
+    c->opt_tile = 1;
+    if (const char* e = getenv("VOF_TILE")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->opt_tile = v; }   // A/B and test default
     c->opt_jac_long_pct = 75;
     c->opt_jacobi_maxt = 0;
     c->opt_fct_x_cols = 2;
@@ -872,6 +877,55 @@ extern "C" int vof2d_interp_velocity(VofCtx* c, float* V_host) {
 }
 
 // ------------------------------------------------------------------------------------
+// Whole-step tile kernel (vof2d_tile.cuh): one launch per step on grids small enough to be launch bound.
+// ------------------------------------------------------------------------------------
+static bool tile_geometry(const VofCtx* c, TileArgs* a, dim3* grid, size_t* smem) {
+    if (c->opt_tile == 0 || c->opt_pressure_solver != 0) return false;
+    if (c->g.gi0 != 0 || c->g.nrows != c->g.nx + 2) return false;                 // full-domain contexts only
+    const int H = c->P.n_jacobi + 5;                                                // dependency radius of one step
+    const int tj = kTileW - 2 * H;
+    if (tj < 8) return false;
+    const int max_th = (int)((227 * 1024) / (10 * kTileW * sizeof(float) + kTileW));   // ten tile arrays + one class byte per cell
+    const int bj = cdiv(c->g.ny + 2, tj);
+    int bi = std::max(1, c->sm_count / bj);                                         // about one block per SM ...
+    int ti = cdiv(c->g.nx + 2, bi);
+    ti = std::max(4, std::min(ti, max_th - 2 * H));                                 // ... as long as the tile fits
+    if (ti + 2 * H > max_th) return false;
+    bi = cdiv(c->g.nx + 2, ti);
+    // by grid size: the tile kernel wins while its blocks are one wave (200^2 2.1x ... 512^2 1.4x); with a second wave
+    // the redundant halo work costs more than the launches save (640^2: 0.8x) -- profiles/exp_tile.py
+    if (c->opt_tile == 1 && (long long)bi * bj > c->sm_count) return false;
+    a->ti = ti; a->tj = tj; a->H = H; a->th = ti + 2 * H; a->n_jacobi = c->P.n_jacobi;
+    *grid = dim3(bj, bi);
+    *smem = (size_t)a->th * kTileW * (10 * sizeof(float) + 1);
+    return true;
+}
+
+static int run_step_tile(VofCtx* c, int istep, TileArgs a, dim3 grid, size_t smem) {
+    Span span_(c, VOF_K_TILE, 2);
+    if (!c->tile_smem_set) {
+        CU(cudaFuncSetAttribute(k_step_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        c->tile_smem_set = 1;
+    }
+    a.u = c->buf[BUF_U]; a.v = c->buf[BUF_V]; a.p = c->p(); a.F = c->F();
+    a.un = c->buf[BUF_RHO]; a.vn = c->buf[BUF_NU]; a.pn = c->p_alt(); a.Fn = c->F_alt();
+    a.us = c->buf[BUF_US]; a.vs = c->buf[BUF_VS]; a.kappa = c->buf[BUF_KAPPA];
+    a.courant_count = &c->diag->courant_count;
+    a.istep = istep;
+    a.d_dx = c->mom.d_dx; a.d_dy = c->mom.d_dy; a.d_dxdy = c->fctx.d_dxdy; a.d_ap0 = c->jac.dv[0]; a.d_ap1 = c->jac.dv[1];
+    a.fast = c->jac.fast_div_ok && c->mom.fast_div_ok && c->fctx.fast_div_ok;
+    CU(cudaMemsetAsync(a.courant_count, 0, sizeof(unsigned long long), c->stream));
+    k_step_tile<<<grid, kTileThreads, smem, c->stream>>>(c->g, c->k, c->jac, a);
+    TRY(launch_ok("k_step_tile"));
+    // the new state lives in the other buffers: F / p ping-pong, u / v exchanged with the (dead) rho / nu buffers
+    c->F_cur ^= 1; c->p_cur ^= 1;
+    std::swap(c->buf[BUF_U], c->buf[BUF_RHO]);
+    std::swap(c->buf[BUF_V], c->buf[BUF_NU]);
+    c->rhs_valid = false;
+    return VOF_OK;
+}
+
+// ------------------------------------------------------------------------------------
 // the loop body 2dvof.py:513-528
 // ------------------------------------------------------------------------------------
 static int step_impl(VofCtx* c, int istep, unsigned flags) {
@@ -893,6 +947,10 @@ static int step_impl(VofCtx* c, int istep, unsigned flags) {
     }
     const bool props = (flags & VOF_STEP_MATERIALIZE_PROPS) != 0;
     const unsigned mask = props ? 31u : 15u;
+    if (!props) {
+        TileArgs ta; dim3 tgrid; size_t tsmem;
+        if (tile_geometry(c, &ta, &tgrid, &tsmem)) return run_step_tile(c, istep, ta, tgrid, tsmem);
+    }
     if (props) TRY(run_cal_nu_rho(c));
     TRY(run_kappa(c));
     TRY(run_advect(c, true));
@@ -1189,6 +1247,7 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
         case VOF_OPT_ADAPTIVE: if (value != 0 && value != 1) return fail(VOF_EINVAL, "adaptive must be 0 or 1"); c->opt_adaptive = value; break;
         case VOF_OPT_JACOBI_LONG_PCT: if (value < 0 || value > 100) return fail(VOF_EINVAL, "jacobi long-item share must be 0 .. 100"); c->opt_jac_long_pct = value; break;
         case VOF_OPT_PRESSURE_SOLVER: if (value != 0 && value != 1) return fail(VOF_EINVAL, "pressure solver must be 0 (Jacobi) or 1 (Chebyshev)"); c->opt_pressure_solver = value; break;
+        case VOF_OPT_TILE: if (value < 0 || value > 2) return fail(VOF_EINVAL, "tile must be 0, 1 or 2"); c->opt_tile = value; break;
         case VOF_OPT_PACKED: if (value != 0 && value != 1) return fail(VOF_EINVAL, "packed must be 0 or 1"); c->opt_packed = value; break;
         case VOF_OPT_JACOBI_PK: if (value != 0 && value != 1) return fail(VOF_EINVAL, "jacobi_pk must be 0 or 1"); c->opt_jacobi_pk = value; break;
         case VOF_OPT_FCT_X_COLS: if (value != 2 && value != 4) return fail(VOF_EINVAL, "fct_x columns per lane must be 2 or 4"); c->opt_fct_x_cols = value; break;

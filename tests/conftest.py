@@ -8,6 +8,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# Small grids default to the whole-step tile kernel (csrc/vof2d_tile.cuh).  The suite was written against the streaming
+# kernels, on small grids for speed: keep it exercising them (tests/test_tile_gpu.py and the tile modes of
+# tests/test_reference_pin_gpu.py select the tile kernel explicitly and check the default policy).
+os.environ.setdefault("VOF_TILE", "0")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
 

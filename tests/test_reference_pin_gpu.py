@@ -59,17 +59,20 @@ def test_cuda_kernels_equal_reference_run_call_by_call_2d(built_lib, name):
             refpin.assert_same(getattr(s, k).to_numpy(), ref[k], f"{name} call {c} ({kname}) field {k}")
 
 
-@pytest.mark.parametrize("mode", ["fused", "graph", "sequence"])
+@pytest.mark.parametrize("mode", ["fused", "graph", "sequence", "tile", "tile_graph"])
 @pytest.mark.parametrize("name", FIX2D)
 def test_cuda_steps_equal_reference_run_2d(built_lib, name, mode):
+    """fused / graph: the streaming kernels; tile / tile_graph: the whole-step tile kernel (one launch per step)."""
+    from taichi_2d_vof_b200 import _lib
     z, meta = refpin.load(name)
     s = _solver2d(z, meta)
+    s.set_option(_lib.VOF_OPT_TILE, 2 if mode.startswith("tile") else 0)
     for t in meta["steps"]:
-        if mode == "graph":
+        if mode.endswith("graph"):
             s.run(t - s.istep)
         else:
             while s.istep < t:
-                s.step() if mode == "fused" else s.step_sequence()
+                s.step_sequence() if mode == "sequence" else s.step()
         for k in (LIVE2D if mode == "sequence" else CORE2D):
             refpin.assert_same(getattr(s, k).to_numpy(), z[f"{k}_{t}"], f"{name} step {t} ({mode}) field {k}")
 
