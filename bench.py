@@ -347,7 +347,7 @@ def run_ours(args):
         a = kern["jacobi"]["algo_GBps"]
         T = kern["jacobi"]["sweeps_per_launch"]
         per = kern["jacobi"]["ms_per_launch"]
-        roof = {"kernel": "k_jacobi_tb<%d> (%g sweeps per HBM pass, register-pipelined)" % (round(T), T), "bound": "hbm",
+        roof = {"kernel": "k_jacobi_pk<%d> (%g sweeps per HBM pass; packed fp32x2 register pipeline, third generation)" % (round(T), T), "bound": "hbm",
                 "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "peak_source": peak_src,
                 "algo_bytes_per_cell_update": 12, "cell_updates_per_launch": cells_per_gpu * T, "ms_per_launch": per,
                 "frac_of_nominal_8TBps": a / 8000.0,
@@ -355,7 +355,7 @@ def run_ours(args):
                 "traffic": None, "traffic_source": tj.get("source"),
                 "note": "frac uses the un-blocked convention (12 B per cell-update): temporal blocking moves ~1/T of those bytes, "
                         "so it may exceed 1; per_pass_frac and dram_frac are the physical fractions"}
-        tb = tj.get("jacobi_tb_bytes_per_launch")
+        tb = tj.get("jacobi_bytes_per_launch", tj.get("jacobi_tb_bytes_per_launch"))
         if tb and not three_d and cells_per_gpu == 8192 * 8192:
             roof["traffic"] = tb
             roof["dram_GBps"] = tb / (per * 1e-3) / 1e9
