@@ -374,6 +374,28 @@ def run_ours(args):
                 "unit": "GB/s", "frac": gbps / peak, "peak_source": peak_src, "algo_bytes_per_cell_step": STEP_BYTES_3D,
                 "frac_of_nominal_8TBps": gbps / 8000.0, "traffic": None}
 
+    # ---- opt-in tolerance mode of the pressure sweeps (VOF_OPT_FAST_MATH: FMA contraction + reciprocal multiply, within the
+    # north-star tolerances but NOT bit-exact -- tests/test_round2_gpu.py): a separate key, never the headline
+    tolerance = None
+    if rank == 0 and world == 1 and not three_d and can_profile:
+        from taichi_2d_vof_b200 import _lib as _vl
+        keep = {k: getattr(s, k).to_numpy() for k in ("u", "v", "p", "F")}
+        s.set_option(_vl.VOF_OPT_FAST_MATH, 1)
+        for _ in range(3):
+            slab.step()
+        k_tol = max(4, min(args.steps, 12))
+        ms_t, _, prof_t = timed_steps(k_tol, 1)
+        s.set_option(_vl.VOF_OPT_FAST_MATH, 0)
+        for k, a_ in keep.items():                      # the exact state goes on (e2e, diagnostics)
+            getattr(s, k).from_numpy(a_)
+        jt = prof_t.get("jacobi")
+        tolerance = {"option": "VOF_OPT_FAST_MATH = 1", "ms_per_step": ms_t / k_tol, "steps": k_tol,
+                     "value": N_JACOBI * cells_total * k_tol / (ms_t * 1e-3) / 1e9, "unit": UNIT,
+                     "jacobi_ms_per_launch": (jt[0] / jt[1]) if jt else None,
+                     "jacobi_per_pass_GBps": (12 * cells_per_gpu / (jt[0] / jt[1] * 1e-3) / 1e9) if jt else None,
+                     "note": "5 instead of 8 fp32 operations per cell-update in the blocked Jacobi; rel. L-inf vs the exact path <= 1e-5 after "
+                             "one step, <= 1e-3 after 100 (tests/test_round2_gpu.py); not used for `value`"}
+
     # ---- e2e: the same step through the host-buffer C-ABI call (pinned memory, developed state)
     e2e = None
     if not args.no_e2e and not three_d:
@@ -501,7 +523,7 @@ def run_ours(args):
             "early_state": early,
             "roofline": roof, "kernels": kern, "kernels_general_path": general,
             "kernel_event_sampling": f"CUDA events around every kernel of every {prof_every}th step of the timed region" if prof_every > 1 else "CUDA events around every kernel of the timed region",
-            "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "gpu_launches": launches,
+            "cpu_baseline": cpu, "e2e": e2e, "tolerance_mode": tolerance, "parity": parity, "gpu_launches": launches,
             "clocks": clk, "state_finite": finite, "mass": d["mass"], "mass_per_rank": d.get("mass_per_rank"), "max_cfl": d["max_cfl"],
         }
         print(json.dumps(line), flush=True)

@@ -193,6 +193,10 @@ enum {
     VOF_OPT_PRESSURE_SOLVER = 9, /* 0 (default): the reference's Jacobi sweeps (2dvof.py:236-266, 521-522); 1: the same number of
                                   sweeps of the Chebyshev semi-iterative acceleration of that iteration -- a stronger
                                   projection for the same traffic per sweep.  Changes p, u, v: outside parity mode */
+    VOF_OPT_FAST_MATH = 12,   /* 0 (default): every operation rounded as the reference's fp32 expression (bit-exact).  1: tolerance mode
+                                  of the blocked pressure sweeps -- fused multiply-adds and a multiply by the reciprocal of the
+                                  diagonal, 5 instead of 8 operations per cell-update; within the north-star tolerances
+                                  (rel. L-inf 1e-5 after one step, 1e-3 after 100), NOT bit-exact */
     VOF_OPT_TILE = 11,        /* whole-step tile kernel for small grids (one launch per step, the step's dependency radius as a
                                   shared-memory halo; csrc/vof2d_tile.cuh): 0 never, 1 (default) where the grid is launch
                                   bound (its blocks are one wave: up to ~520^2 on 148 SMs), 2 whenever the tile fits; same bits.

@@ -82,6 +82,7 @@ struct VofCtx {
     int jac_resident_warps_pk[6];
     int opt_jac_long_pct;      // third-generation Jacobi: share of the rows (percent) cut into one long item per resident warp
     int opt_pressure_solver;   // 0 (default): the reference's Jacobi sweeps; 1: Chebyshev-accelerated Jacobi (changes p: outside parity mode)
+    int opt_fast_math;         // 1: tolerance mode of the blocked Jacobi (opt-in, not bit-exact; vof2d_jacobi_pk.cuh: pk_step_fast)
     int opt_tile;              // whole-step tile kernel (vof2d_tile.cuh): 0 never, 1 by grid size (default), 2 whenever it fits
     int tile_smem_set;
     int opt_packed;            // 1 (default): packed fp32x2 arithmetic in the streaming kernels that have it (same bits)
@@ -520,10 +521,11 @@ static int run_jacobi_sweep(VofCtx* c, int rhs_mode) {
 // Third generation (packed fp32x2 arithmetic, c*p products, cp.async rings; vof2d_jacobi_pk.cuh)
 template <int T>
 static int launch_jacobi_pk(VofCtx* c, const float* pin, float* pout) {
-    auto kern_pk = k_jacobi_pk<T>;
+    auto kern_pk = c->opt_fast_math ? k_jacobi_pk<T, true> : k_jacobi_pk<T, false>;
     if (!c->jac_resident_warps_pk[T]) {
         int nb = 0;
-        CU(cudaFuncSetAttribute(kern_pk, cudaFuncAttributeMaxDynamicSharedMemorySize, kPkSmem));
+        CU(cudaFuncSetAttribute(k_jacobi_pk<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPkSmem));
+        CU(cudaFuncSetAttribute(k_jacobi_pk<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPkSmem));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern_pk, 32 * kPkWarps, kPkSmem));
         c->jac_resident_warps_pk[T] = std::max(1, nb) * kPkWarps * c->sm_count;
     }
@@ -1247,6 +1249,7 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
         case VOF_OPT_ADAPTIVE: if (value != 0 && value != 1) return fail(VOF_EINVAL, "adaptive must be 0 or 1"); c->opt_adaptive = value; break;
         case VOF_OPT_JACOBI_LONG_PCT: if (value < 0 || value > 100) return fail(VOF_EINVAL, "jacobi long-item share must be 0 .. 100"); c->opt_jac_long_pct = value; break;
         case VOF_OPT_PRESSURE_SOLVER: if (value != 0 && value != 1) return fail(VOF_EINVAL, "pressure solver must be 0 (Jacobi) or 1 (Chebyshev)"); c->opt_pressure_solver = value; break;
+        case VOF_OPT_FAST_MATH: if (value != 0 && value != 1) return fail(VOF_EINVAL, "fast_math must be 0 or 1"); c->opt_fast_math = value; break;
         case VOF_OPT_TILE: if (value < 0 || value > 2) return fail(VOF_EINVAL, "tile must be 0, 1 or 2"); c->opt_tile = value; break;
         case VOF_OPT_PACKED: if (value != 0 && value != 1) return fail(VOF_EINVAL, "packed must be 0 or 1"); c->opt_packed = value; break;
         case VOF_OPT_JACOBI_PK: if (value != 0 && value != 1) return fail(VOF_EINVAL, "jacobi_pk must be 0 or 1"); c->opt_jacobi_pk = value; break;

@@ -91,6 +91,10 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+constexpr f32x2 kNegZero2 = 0x8000000080000000ull, kOne2 = 0x3f8000003f800000ull;
+// literal forms: ptxas may fuse them with their neighbours (tolerance-mode code only)
+__device__ __forceinline__ f32x2 loose_mul2(f32x2 a, f32x2 b) { return fma2(a, b, kNegZero2); }
+__device__ __forceinline__ f32x2 loose_add2(f32x2 a, f32x2 b) { return fma2(a, kOne2, b); }
 // With LITERAL 1 and -0 ptxas rewrites the two forms above to FADD2 / FMUL2 and then contracts an adjacent FMUL2 + FADD2
 // pair into one FFMA2 -- even under -fmad=false (seen in SASS; three cells of a 300 x 700 step differed).  The operations
 // of a kernel whose products feed sums directly therefore take 1 and -0 from kernel parameters (Consts::one, neg_zero):
