@@ -1,4 +1,4 @@
-"""`python profiles/sass_mnemonics.py > profiles/r1_sass_mnemonics.md` -- static evidence from the built library (no GPU):
+"""`python profiles/sass_mnemonics.py > profiles/r2_sass_mnemonics.md` -- static evidence from the built library (no GPU):
 per kernel of libvof.so the SASS instruction count and the mnemonics that show how it moves data (cp.async = LDGSTS,
 128-bit global accesses, shuffles, shared-memory loads, queue atomics, barriers) and how it divides (MUFU.RCP + FCHK =
 nvcc's IEEE division, DFMA = the fp64 sub-normal path)."""
@@ -20,7 +20,7 @@ for line in res.splitlines():
     m = re.search(r"REG:(\d+).*?SHARED:(\d+)", line)
     if m and cur:
         regs[cur] = (int(m.group(1)), int(m.group(2)))
-keys = ["LDGSTS", "LDG.E.128", "LDG.E.64", "STG.E.128", "STG.E.64", "LDS", "SHFL", "VOTE", "ATOMG", "BAR.SYNC", "MUFU.RCP", "FCHK", "DFMA", "FFMA"]
+keys = ["LDGSTS", "LDG.E.128", "LDG.E.64", "STG.E.128", "STG.E.64", "LDS", "SHFL", "VOTE", "ATOMG", "BAR.SYNC", "MUFU.RCP", "FCHK", "DFMA", "FFMA2", "FMUL2", "FADD2", "FFMA"]
 stats = collections.OrderedDict()
 name = None
 for line in sass.splitlines():
@@ -34,7 +34,7 @@ for line in sass.splitlines():
         op = m.group(1)
         stats[name]["n"] += 1
         for k in keys:
-            if op.startswith(k):
+            if op.startswith(k) and not (k == "FFMA" and op.startswith("FFMA2")):      # FFMA2 / FMUL2 / FADD2: Blackwell packed fp32
                 stats[name][k] += 1
 demangled = subprocess.run(["c++filt"], input="\n".join(stats), capture_output=True, text=True).stdout.splitlines()
 print("# SASS mnemonics per kernel of libvof.so (sm_100a; `python profiles/sass_mnemonics.py`)\n")
