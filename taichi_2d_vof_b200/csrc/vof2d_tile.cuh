@@ -12,9 +12,11 @@
 // loop bounds (the per-cell forms are those of oracle/vof2d_oracle.c, which is pinned to the reference run), so the
 // result is bit-identical to the streaming path -- tests/test_tile_gpu.py.
 //
-// Blocks read the old state (u, v, p, F, and the never-written entries of u*, v*) from one set of buffers and write
-// the new state into another (F / p ping-pong as everywhere; u, v into the rho / nu buffers, which the fused step does
-// not use -- the host swaps the pointers), so there is no inter-block hazard and no grid-wide barrier.
+// Blocks read the old state (u, v, p, F) from one set of buffers and write the new state into another (F / p ping-pong
+// as everywhere; u, v into the rho / nu buffers, which the fused step does not use -- the host swaps the pointers).
+// u*, v* and kappa are updated in place: a block stores only the entries it owns and loads only entries that no block
+// ever stores (the rows / columns outside advect_upwind's loop ranges), so there is no inter-block hazard and no
+// grid-wide barrier.
 #pragma once
 #include "vof2d_jacobi_tb.cuh"
 #include "vof_common.cuh"
@@ -81,7 +83,10 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
         const bool ex = gi >= 0 && gi <= nx + 1 && gj >= 0 && gj <= ny + 1;
         const size_t o = ex ? (size_t)gi * P + gj : 0;
         m.u[c] = ex ? a.u[o] : 0.0f; m.v[c] = ex ? a.v[o] : 0.0f; m.p[c] = ex ? a.p[o] : 0.0f; m.F[c] = ex ? a.F[o] : 0.0f;
-        m.us[c] = ex ? a.us[o] : 0.0f; m.vs[c] = ex ? a.vs[o] : 0.0f;
+        // u*, v* are updated in place: only their never-written entries (outside the loop ranges of 2dvof.py:208, 221 --
+        // stable, nobody stores to them) are loaded; every entry inside the ranges is recomputed here before it is used
+        const bool us_loop = gi >= 2 && gi <= nx && gj >= 1 && gj <= ny, vs_loop = gi >= 1 && gi <= nx && gj >= 2 && gj <= ny;
+        m.us[c] = (ex && !us_loop) ? a.us[o] : 0.0f; m.vs[c] = (ex && !vs_loop) ? a.vs[o] : 0.0f;
         m.pB[c] = 0.0f; m.FB[c] = 0.0f;          // mx, my: never-written entries are 0 (2dvof.py:80-81)
         m.kap[c] = 0.0f; m.rhs[c] = 0.0f;
         unsigned q = 0;
@@ -370,7 +375,9 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
         if (!(cls[c] & T_OWN)) return;
         const size_t o = (size_t)(gi0 + (c >> 6)) * P + gj0 + (c & 63);
         a.un[o] = m.u[c]; a.vn[o] = m.v[c]; a.pn[o] = m.p[c]; a.Fn[o] = m.F[c];
-        a.us[o] = m.us[c]; a.vs[o] = m.vs[c];
+        const unsigned q = cls[c];
+        if ((q & (T_IN | T_I2)) == (T_IN | T_I2)) a.us[o] = m.us[c];          // the entries advect_upwind writes, no others
+        if ((q & (T_IN | T_J2)) == (T_IN | T_J2)) a.vs[o] = m.vs[c];
     });
 }
 
