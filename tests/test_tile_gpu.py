@@ -69,6 +69,20 @@ def test_tile_step_on_live_states_equals_oracle(built_lib, shape, n_jacobi, seed
         _same(s, o, f"{shape} n_jacobi {n_jacobi} step {step}")
 
 
+@pytest.mark.parametrize("nx,ny,Lx,Ly,n_jacobi", [(96, 64, 0.1, 0.1, 10), (50, 120, 0.05, 0.03, 4), (70, 70, 0.035, 0.035, 0), (70, 70, 0.035, 0.035, 1)])
+def test_tile_step_non_square_cells_and_few_sweeps(built_lib, nx, ny, Lx, Ly, n_jacobi):
+    """dx != dy (the Poisson coefficients differ by direction) and the shallow halos of n_jacobi = 0, 1."""
+    P = Vof2DParams(nx=nx, ny=ny, Lx=Lx, Ly=Ly, n_jacobi=n_jacobi)
+    F, u, v, p = _live_state(nx, ny, 9, 0.2, P)
+    o = Vof2DOracle(P)
+    s = _solver(P, 2)
+    for k, a in (("F", F), ("u", u), ("v", v), ("p", p)):
+        getattr(o, k)[...] = a; getattr(s, k).from_numpy(a)
+    for step in range(1, 4):
+        o.step(); s.step()
+        _same(s, o, f"{nx}x{ny} L=({Lx},{Ly}) n_jacobi {n_jacobi} step {step}")
+
+
 def test_tile_and_streaming_paths_interleave(built_lib):
     """Tile steps exchange the u / v buffers with the (dead) rho / nu buffers and flip F / p; streaming steps, single
     kernel entries and graph replay in between must keep working on the live buffers."""
