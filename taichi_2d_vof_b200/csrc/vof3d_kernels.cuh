@@ -466,7 +466,7 @@ k3_jacobi4(Grid3 g, Consts3 c, Jac3C jc, const float* __restrict__ p, float* __r
 // per warp (an, as) and per lane (af, ab); the constant-divisor quotient for every cell plus an IEEE division only on
 // the cells whose diagonal differs; one warp-level fix-up for sub-normal quotients; everything row i+1 needs is
 // requested while row i is computed; strips cover interior columns only (the lane next to a ghost column copies it).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 7)      // 70 registers, 28 warps per SM: 512^3 step 7.14 -> 6.60 ms (6 blocks: 6.85, 8 blocks spill: 7.21)
 k3_jacobi5(Grid3 g, Consts3 c, Jac3C jc, const float* __restrict__ p, float* __restrict__ pn, const float* __restrict__ rhs,
            int r0, int r1, int rows_per_block) {
     const int lane = threadIdx.x & 31;
