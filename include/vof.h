@@ -193,6 +193,9 @@ enum {
     VOF_OPT_PRESSURE_SOLVER = 9, /* 0 (default): the reference's Jacobi sweeps (2dvof.py:236-266, 521-522); 1: the same number of
                                   sweeps of the Chebyshev semi-iterative acceleration of that iteration -- a stronger
                                   projection for the same traffic per sweep.  Changes p, u, v: outside parity mode */
+    VOF_OPT_BARE_DIV = 13,    /* 1 (default): where vof2d_create proved the three-operation reciprocal division exact for EVERY fp32
+                                  numerator of the Poisson diagonal (all 2^32 patterns, sub-normal quotients included), the packed
+                                  Jacobi runs without the sub-normal test and its fp64 fix-up; 0: always with them (A/B); same bits */
     VOF_OPT_FAST_MATH = 12,   /* 0 (default): every operation rounded as the reference's fp32 expression (bit-exact).  1: tolerance mode
                                   of the blocked pressure sweeps -- fused multiply-adds and a multiply by the reciprocal of the
                                   diagonal, 5 instead of 8 operations per cell-update; within the north-star tolerances

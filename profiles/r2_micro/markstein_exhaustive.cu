@@ -1,0 +1,45 @@
+// Is the bare 3-operation Markstein division q = RN(t r), q' = fma(fma(-q, b, t), r, q) the correctly rounded t / b for EVERY fp32
+// numerator -- sub-normal numerators and quotients included -- for the Poisson diagonals of the BASELINE configurations?
+// Exhaustive: all 2^32 bit patterns per divisor.  nvcc -arch=sm_100a -fmad=false -o markstein_exhaustive markstein_exhaustive.cu
+#include <cstdio>
+#include <cmath>
+#include <cuda_runtime.h>
+__global__ void check(float b, float r, unsigned long long* bad, unsigned long long* bad_tiny, unsigned int* first) {
+    unsigned long long nb = 0, nt = 0;
+    for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < (1ull << 32); k += (unsigned long long)gridDim.x * blockDim.x) {
+        const float t = __uint_as_float((unsigned)k);
+        if (!(fabsf(t) <= 1.2676506002282294e30f)) continue;      // 2^100; skips NaN / inf
+        const float q = t * r;
+        const float e = __fmaf_rn(-q, b, t);
+        const float a = __fmaf_rn(e, r, q);
+        const float x = __fdiv_rn(t, b);
+        if (__float_as_uint(a) != __float_as_uint(x)) { ++nb; if (fabsf(t) < 7.8886090522101181e-31f) ++nt; atomicMin(first, (unsigned)k & 0x7fffffffu); }
+    }
+    if (nb) atomicAdd(bad, nb);
+    if (nt) atomicAdd(bad_tiny, nt);
+}
+static float diag(double dx, int walls_i, int walls_j) {
+    const float c = (float)((1.0 / dx) * (1.0 / dx));
+    const float ae = c, aw = walls_i ? 0.0f : c, an = c, as = walls_j ? 0.0f : c;
+    volatile float s = ae + aw; s = s + an; s = s + as;
+    return -1.0f * s;
+}
+int main() {
+    unsigned long long *bad, *badt; unsigned int* first;
+    cudaMallocManaged(&bad, 8); cudaMallocManaged(&badt, 8); cudaMallocManaged(&first, 4);
+    // dx as the library derives it: difference of two fp32 node coordinates, L = 0.1 * n / 200 (scaled) or 0.1 (reference 200^2)
+    const int ns[] = {200, 2048, 8192, 32768};
+    for (int n : ns) {
+        const double L = 0.1 * n / 200;
+        const float x3 = (float)(L * 2 / n), x2 = (float)(L * 1 / n);
+        const double dx = (double)x3 - (double)x2;
+        for (int wi = 0; wi < 2; ++wi) for (int wj = 0; wj < 2; ++wj) {
+            const float b = diag(dx, wi, wj), r = 1.0f / b;
+            *bad = 0; *badt = 0; *first = 0xffffffffu;
+            check<<<148 * 8, 256>>>(b, r, bad, badt, first);
+            cudaDeviceSynchronize();
+            printf("n %5d  dx %.9g  diagonal[%d][%d] %.9g : %llu mismatches (%llu with |t| < 2^-100), smallest |t| bits 0x%08x\n", n, dx, wi, wj, b, *bad, *badt, *first);
+        }
+    }
+    return 0;
+}

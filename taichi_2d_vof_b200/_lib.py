@@ -31,6 +31,7 @@ VOF_OPT_PRESSURE_SOLVER = 9
 VOF_OPT_PACKED = 10
 VOF_OPT_TILE = 11
 VOF_OPT_FAST_MATH = 12
+VOF_OPT_BARE_DIV = 13
 VOF_VIEW_VOF, VOF_VIEW_U, VOF_VIEW_V, VOF_VIEW_VNORM = 0, 1, 2, 3
 VOF_STEP_MATERIALIZE_PROPS = 1
 VOF_STEP_NO_FUSION = 2

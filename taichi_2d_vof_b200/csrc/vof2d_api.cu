@@ -82,6 +82,7 @@ struct VofCtx {
     int jac_resident_warps_pk[6];
     int opt_jac_long_pct;      // third-generation Jacobi: share of the rows (percent) cut into one long item per resident warp
     int opt_pressure_solver;   // 0 (default): the reference's Jacobi sweeps; 1: Chebyshev-accelerated Jacobi (changes p: outside parity mode)
+    int opt_bare_div;          // 1 (default): use the bare division where it is proven (0: always test for tiny numerators; A/B)
     int opt_fast_math;         // 1: tolerance mode of the blocked Jacobi (opt-in, not bit-exact; vof2d_jacobi_pk.cuh: pk_step_fast)
     int opt_tile;              // whole-step tile kernel (vof2d_tile.cuh): 0 never, 1 by grid size (default), 2 whenever it fits
     int tile_smem_set;
@@ -152,12 +153,12 @@ extern "C" size_t vof2d_arena_bytes(const VofParams* p) {
 // Proof that the reciprocal division by `d` is exact: every fp32 numerator against __fdiv_rn (4.8 ms per divisor).
 // The verdict depends on the divisor (and the device executing it) only, so it is cached: the 16 slab contexts of a
 // streamer, or repeated solver creation in a test session, prove each constant once.
-static int const_div_exact(VofCtx* c, const ConstDiv& d, bool* ok) {
+static int const_div_exact(VofCtx* c, const ConstDiv& d, bool* ok, int bare = 0) {
     static std::mutex mu;
-    static std::map<std::pair<int, unsigned int>, bool> verdicts;
+    static std::map<std::pair<int, unsigned long long>, bool> verdicts;
     unsigned int bits;
     memcpy(&bits, &d.b, sizeof(bits));
-    const std::pair<int, unsigned int> key(c->device, bits);
+    const std::pair<int, unsigned long long> key(c->device, ((unsigned long long)bare << 32) | bits);
     {
         std::lock_guard<std::mutex> lock(mu);
         auto it = verdicts.find(key);
@@ -166,7 +167,7 @@ static int const_div_exact(VofCtx* c, const ConstDiv& d, bool* ok) {
     unsigned long long* bad = &c->diag->courant_count;
     unsigned long long h = 1;
     CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
-    k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(d, bad);
+    k_check_div_by_const<<<c->sm_count * 8, 256, 0, c->stream>>>(d, bad, bare);
     CU(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
@@ -261,6 +262,7 @@ static int create_impl(const VofParams* in, void* arena, size_t arena_bytes, Vof
     c->opt_jacobi_pk = 1;
     c->opt_packed = 1;
     c->opt_tile = 1;
+    c->opt_bare_div = 1;
     if (const char* e = getenv("VOF_TILE")) { const int v = atoi(e); if (v >= 0 && v <= 2) c->opt_tile = v; }   // A/B and test default
     c->opt_jac_long_pct = 75;
     c->opt_jacobi_maxt = 0;
@@ -309,6 +311,12 @@ static int create_finish(VofCtx* c, void* arena, size_t arena_bytes, const std::
         bool a = false, b = false;
         TRY(const_div_exact(c, c->jac.dv[0], &a)); TRY(const_div_exact(c, c->jac.dv[1], &b));
         c->jac.fast_div_ok = a && b;
+        c->jac.bare_div_ok = 0;
+        if (a && b) {       // the bare form for the packed Jacobi (no sub-normal test, no fix-up): every numerator again
+            bool a2 = false, b2 = false;
+            TRY(const_div_exact(c, c->jac.dv[0], &a2, 1)); TRY(const_div_exact(c, c->jac.dv[1], &b2, 1));
+            c->jac.bare_div_ok = a2 && b2;
+        }
         TRY(const_div_exact(c, c->fctx.d_dxdy, &a)); TRY(const_div_exact(c, c->fctx.d_dy, &b));
         c->fctx.fast_div_ok = c->fcty.fast_div_ok = a && b;
         TRY(const_div_exact(c, c->mom.d_dx, &a)); TRY(const_div_exact(c, c->mom.d_dy, &b));
@@ -521,11 +529,16 @@ static int run_jacobi_sweep(VofCtx* c, int rhs_mode) {
 // Third generation (packed fp32x2 arithmetic, c*p products, cp.async rings; vof2d_jacobi_pk.cuh)
 template <int T>
 static int launch_jacobi_pk(VofCtx* c, const float* pin, float* pout) {
-    auto kern_pk = c->opt_fast_math ? k_jacobi_pk<T, true> : k_jacobi_pk<T, false>;
+    // <tolerance mode, bare division>: the bare variant when the context proved it for both interior-row diagonals
+    const bool bare = c->jac.bare_div_ok && c->opt_bare_div;
+    auto kern_pk = c->opt_fast_math ? (bare ? k_jacobi_pk<T, true, true> : k_jacobi_pk<T, true, false>)
+                                    : (bare ? k_jacobi_pk<T, false, true> : k_jacobi_pk<T, false, false>);
     if (!c->jac_resident_warps_pk[T]) {
         int nb = 0;
-        CU(cudaFuncSetAttribute(k_jacobi_pk<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPkSmem));
-        CU(cudaFuncSetAttribute(k_jacobi_pk<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPkSmem));
+        CU(cudaFuncSetAttribute(k_jacobi_pk<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPkSmem));
+        CU(cudaFuncSetAttribute(k_jacobi_pk<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPkSmem));
+        CU(cudaFuncSetAttribute(k_jacobi_pk<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPkSmem));
+        CU(cudaFuncSetAttribute(k_jacobi_pk<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPkSmem));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern_pk, 32 * kPkWarps, kPkSmem));
         c->jac_resident_warps_pk[T] = std::max(1, nb) * kPkWarps * c->sm_count;
     }
@@ -1249,6 +1262,7 @@ extern "C" int vof2d_set_option(VofCtx* c, int option, int value) {
         case VOF_OPT_ADAPTIVE: if (value != 0 && value != 1) return fail(VOF_EINVAL, "adaptive must be 0 or 1"); c->opt_adaptive = value; break;
         case VOF_OPT_JACOBI_LONG_PCT: if (value < 0 || value > 100) return fail(VOF_EINVAL, "jacobi long-item share must be 0 .. 100"); c->opt_jac_long_pct = value; break;
         case VOF_OPT_PRESSURE_SOLVER: if (value != 0 && value != 1) return fail(VOF_EINVAL, "pressure solver must be 0 (Jacobi) or 1 (Chebyshev)"); c->opt_pressure_solver = value; break;
+        case VOF_OPT_BARE_DIV: if (value != 0 && value != 1) return fail(VOF_EINVAL, "bare_div must be 0 or 1"); c->opt_bare_div = value; break;
         case VOF_OPT_FAST_MATH: if (value != 0 && value != 1) return fail(VOF_EINVAL, "fast_math must be 0 or 1"); c->opt_fast_math = value; break;
         case VOF_OPT_TILE: if (value < 0 || value > 2) return fail(VOF_EINVAL, "tile must be 0, 1 or 2"); c->opt_tile = value; break;
         case VOF_OPT_PACKED: if (value != 0 && value != 1) return fail(VOF_EINVAL, "packed must be 0 or 1"); c->opt_packed = value; break;

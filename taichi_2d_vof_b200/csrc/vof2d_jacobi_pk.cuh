@@ -86,7 +86,9 @@ __device__ __noinline__ float4 pk_fix_tiny(float4 t, float4 q, double bd, double
 // through every sweep unchanged (ghost cells are not swept), wall-adjacent columns divide by their own diagonal, the
 // two wall rows go through the IEEE division with theirs.  Per-lane masks and selects instead of per-lane constants:
 // these items are ~5 % of the work and must not cost the bulk loop registers.
-template <int T, int PH, bool EDGE, bool WALL>
+// BARE: the context proved the three-operation division exact for every fp32 numerator of this divisor (create: all 2^32
+// patterns, JacTB::bare_div_ok), so the sub-normal test and its fp64 fix-up are not compiled in.
+template <int T, int PH, bool EDGE, bool WALL, bool BARE>
 __device__ __forceinline__ void pk_step(JacPk<T>& S, const PkLane& L, const float4 pin, const int R, const unsigned rcur,
                                         const PkConsts& k, const JacTB& jc, const Grid& g, const int jl,
                                         float* __restrict__ pout, const int ra, const int rb, const bool store_lane) {
@@ -156,8 +158,8 @@ __device__ __forceinline__ void pk_step(JacPk<T>& S, const PkLane& L, const floa
             float t0, t1, t2, t3;
             unpk2(tA, t0, t1);
             unpk2(tB, t2, t3);
-            const unsigned key = min(min(tiny_key(t0), tiny_key(t1)), min(tiny_key(t2), tiny_key(t3)));
-            if (key < kTinyKey) {           // the fp32 residual would underflow: same scheme in fp64 (rare: the pressure front)
+            const unsigned key = BARE ? 0xffffffffu : min(min(tiny_key(t0), tiny_key(t1)), min(tiny_key(t2), tiny_key(t3)));
+            if (!BARE && key < kTinyKey) {  // the fp32 residual would underflow: same scheme in fp64 (rare: the pressure front)
                 float q0, q1, q2, q3;
                 unpk2(qA, q0, q1);
                 unpk2(qB, q2, q3);
@@ -244,7 +246,7 @@ __device__ __forceinline__ void pk_step_fast(JacPk<T>& S, const float4 pin, cons
 }
 
 // one (strip, rows) item
-template <int T, bool EDGE, bool WALL, bool FAST = false>
+template <int T, bool EDGE, bool WALL, bool FAST, bool BARE>
 __device__ __forceinline__ void pk_run_impl(const Grid& g, const JacTB& jc, const float* __restrict__ p, float* __restrict__ pout,
                                             const float* __restrict__ rhs, const int ra, const int rb, const int jstrip, const int lane,
                                             const unsigned pbase, const unsigned rbase) {
@@ -297,7 +299,7 @@ __device__ __forceinline__ void pk_run_impl(const Grid& g, const JacTB& jc, cons
             pk_step_fast<T, PH>(S, pin, R, rbase + (unsigned)((R & (kPkRSlots - 1)) + kPkRSlots) * kPkRowBytes,  \
                                 pk2(-jc.cx), pk2(jc.dv[0].r), P, jl, pout, ra, rb, store_lane);                  \
         else                                                                                                     \
-            pk_step<T, PH, EDGE, WALL>(S, L, pin, R, rbase + (unsigned)((R & (kPkRSlots - 1)) + kPkRSlots) * kPkRowBytes, \
+            pk_step<T, PH, EDGE, WALL, BARE>(S, L, pin, R, rbase + (unsigned)((R & (kPkRSlots - 1)) + kPkRSlots) * kPkRowBytes, \
                                        k, jc, g, jl, pout, ra, rb, store_lane);                                  \
         ++R;                                                                                                     \
     }
@@ -328,7 +330,7 @@ struct PkSched {
 
 // Persistent warps pull items from a queue (the cost of an item is data dependent).  Square cells and reciprocal
 // divisions proven exact are the host's precondition (launch_jacobi_tb).
-template <int T, bool FAST = false>
+template <int T, bool FAST, bool BARE>
 __global__ void __launch_bounds__(32 * kPkWarps, kPkBlocksPerSM)
 k_jacobi_pk(Grid g, JacTB jc, PkSched sc, const float* __restrict__ p, float* __restrict__ pout, const float* __restrict__ rhs,
             int r0, int r1) {
@@ -372,9 +374,9 @@ k_jacobi_pk(Grid g, JacTB jc, PkSched sc, const float* __restrict__ p, float* __
         const bool strip_interior = jstrip >= 2 && jstrip + kJacStripCols - 1 <= g.ny - 1;
         // every row the pipeline touches (ra - T .. rb + T, minus the sweeps' skew) strictly inside the i-walls?
         const bool wallrows = g.gi0 + ra - T - T < 2 || g.gi0 + rb + T > g.nx - 1;
-        if (wallrows) pk_run_impl<T, true, true>(g, jc, p, pout, rhs, ra, rb, jstrip, lane, pbase, rbase);
-        else if (!strip_interior) pk_run_impl<T, true, false>(g, jc, p, pout, rhs, ra, rb, jstrip, lane, pbase, rbase);
-        else pk_run_impl<T, false, false, FAST>(g, jc, p, pout, rhs, ra, rb, jstrip, lane, pbase, rbase);
+        if (wallrows) pk_run_impl<T, true, true, false, BARE>(g, jc, p, pout, rhs, ra, rb, jstrip, lane, pbase, rbase);
+        else if (!strip_interior) pk_run_impl<T, true, false, false, BARE>(g, jc, p, pout, rhs, ra, rb, jstrip, lane, pbase, rbase);
+        else pk_run_impl<T, false, false, FAST, BARE>(g, jc, p, pout, rhs, ra, rb, jstrip, lane, pbase, rbase);
     }
 }
 

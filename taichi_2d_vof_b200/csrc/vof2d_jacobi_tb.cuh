@@ -61,10 +61,14 @@ struct JacTB {
     float ap[2][2];        // -(ae+aw+an+as) by [row touches an i-wall][column touches a j-wall]
     ConstDiv dv[2];        // division by ap[0][jc]
     int fast_div_ok;       // reciprocal division validated for ap[0][0] and ap[0][1]
+    int bare_div_ok;       // ... and the bare three-operation form (no sub-normal fix-up) proven exact for EVERY fp32 numerator
 };
 
-// exhaustive check of div_by_const against IEEE division: every fp32 bit pattern
-static __global__ void k_check_div_by_const(ConstDiv d, unsigned long long* mismatches) {
+// exhaustive check of div_by_const against IEEE division: every fp32 bit pattern.  bare: the three operations alone, with no
+// fp64 path for tiny numerators -- for most divisors they are exact there too (the residual t - q b is a multiple of the
+// smallest sub-normal and therefore always representable; what can fail is the final rounding of a sub-normal quotient
+// next to a tie), and a kernel that has this proof for its divisor needs neither the test nor the fix-up.
+static __global__ void k_check_div_by_const(ConstDiv d, unsigned long long* mismatches, int bare) {
     const unsigned long long n = 1ull << 32;
     unsigned long long bad = 0;
     for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n;
@@ -72,7 +76,7 @@ static __global__ void k_check_div_by_const(ConstDiv d, unsigned long long* mism
         const float t = __uint_as_float((unsigned)k);
         const float at = fabsf(t);
         if (!(at <= 1.2676506002282294e30f)) continue;       // 2^100; also skips NaN
-        const float a = div_by_const(t, d), e = __fdiv_rn(t, d.b);
+        const float a = bare ? div_by_const_core(t, d.b, d.r) : div_by_const(t, d), e = __fdiv_rn(t, d.b);
         bad += (__float_as_uint(a) != __float_as_uint(e));
     }
     if (bad) atomicAdd(mismatches, bad);

@@ -164,7 +164,7 @@ extern "C" int vof3d_create(const VofParams* in, Vof3Ctx** out) {
     {   // prove the reciprocal division by the interior diagonal exact (every fp32 numerator against __fdiv_rn)
         unsigned long long* bad = &c->diag->courant_count;
         c->sm_count = prop.multiProcessorCount;
-        k_check_div_by_const<<<prop.multiProcessorCount * 8, 256, 0, c->stream>>>(c->jac.dv, bad);
+        k_check_div_by_const<<<prop.multiProcessorCount * 8, 256, 0, c->stream>>>(c->jac.dv, bad, 0);
         unsigned long long h = 1;
         CU(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
