@@ -929,6 +929,7 @@ static int run_step_tile(VofCtx* c, int istep, TileArgs a, dim3 grid, size_t sme
     a.istep = istep;
     a.d_dx = c->mom.d_dx; a.d_dy = c->mom.d_dy; a.d_dxdy = c->fctx.d_dxdy; a.d_ap0 = c->jac.dv[0]; a.d_ap1 = c->jac.dv[1];
     a.fast = c->jac.fast_div_ok && c->mom.fast_div_ok && c->fctx.fast_div_ok;
+    a.bare = a.fast && c->jac.bare_div_ok && c->opt_bare_div;
     CU(cudaMemsetAsync(a.courant_count, 0, sizeof(unsigned long long), c->stream));
     k_step_tile<<<grid, kTileThreads, smem, c->stream>>>(c->g, c->k, c->jac, a);
     TRY(launch_ok("k_step_tile"));

@@ -35,7 +35,8 @@ struct TileArgs {
     int H, th;                  // halo; tile height th = ti + 2 H (tile width is kTileW = tj + 2 H)
     int n_jacobi, istep;
     ConstDiv d_dx, d_dy, d_dxdy, d_ap0, d_ap1;     // exact reciprocal division by dx, dy, dx dy and the Poisson diagonal of an
-    int fast;                                      // interior row (away from / next to a j-wall); proven at vof2d_create
+    int fast, bare;                                // interior row (away from / next to a j-wall); proven at vof2d_create; bare: the
+                                                   // Poisson diagonals need no sub-normal fix-up either (JacTB::bare_div_ok)
 };
 
 // cell classes, computed once per step (one byte per tile cell) instead of index arithmetic in each of the ~30 phases
@@ -47,6 +48,9 @@ enum : unsigned { T_IN = 1u,      // interior cell (1 <= i <= nx, 1 <= j <= ny) 
                   T_WJ = 32u };   // next to a j-wall
 
 __device__ __forceinline__ float tdiv(float t, const ConstDiv& d, int fast) { return fast ? div_by_const(t, d) : div_nz(t, d.b); }
+__device__ __forceinline__ float tdiv_ap(float t, const ConstDiv& d, int fast, int bare) {
+    return bare ? div_by_const_core(t, d.b, d.r) : tdiv(t, d, fast);
+}
 
 // The ten tile arrays.  Scratch use: mx / my live in pB / FB until the curvature is done; Ftd / rp / rm live in
 // rhs / kap / pB during the FCT sweeps (kappa has been written out, the pressure iteration is over).
@@ -234,7 +238,7 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
                 t = t - k.dxi2 * pc[c - kTileW];
                 t = t - k.dyi2 * pc[c + 1];
                 t = t - k.dyi2 * pc[c - 1];
-                out = tdiv(t, a.d_ap0, a.fast);
+                out = tdiv_ap(t, a.d_ap0, a.fast, a.bare);
             } else {
                 const int gi = gi0 + (c >> 6), gj = gj0 + (c & 63);
                 const float ae = gi != nx ? k.dxi2 : 0.0f, aw = gi != 1 ? k.dxi2 : 0.0f;
@@ -245,7 +249,7 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
                 t = t - aw * pc[c - kTileW];
                 t = t - an * pc[c + 1];
                 t = t - as * pc[c - 1];
-                out = (!wi) ? tdiv(t, a.d_ap1, a.fast) : div_nz(t, ap);
+                out = (!wi) ? tdiv_ap(t, a.d_ap1, a.fast, a.bare) : div_nz(t, ap);
             }
             pn[c] = out;
         });

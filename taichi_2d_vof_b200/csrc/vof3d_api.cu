@@ -170,6 +170,15 @@ extern "C" int vof3d_create(const VofParams* in, Vof3Ctx** out) {
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
         c->jac.fast_div_ok = (h == 0);
+        c->jac.bare_div_ok = 0;
+        if (h == 0) {           // the bare three-operation form, every numerator again: no sub-normal test in the sweep if it holds
+            k_check_div_by_const<<<prop.multiProcessorCount * 8, 256, 0, c->stream>>>(c->jac.dv, bad, 1);
+            unsigned long long h2 = 1;
+            CU(cudaMemcpyAsync(&h2, bad, sizeof(h2), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            CU(cudaMemsetAsync(bad, 0, sizeof(*bad), c->stream));
+            c->jac.bare_div_ok = (h2 == 0);
+        }
     }
     *out = c;
     return VOF_OK;
@@ -261,7 +270,8 @@ static int run3_jacobi(Vof3Ctx* c, int mode) {
         if (c->opt_gen2) {
             const int rows = std::max(1, std::min(c->opt_jac_rows, planes));
             dim3 g5(cdiv(c->g.nz, 128), cdiv(c->g.ny + 2, 4), cdiv(planes, rows));
-            k3_jacobi5<<<g5, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, rows);
+            if (c->jac.bare_div_ok) k3_jacobi5<true><<<g5, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, rows);
+            else k3_jacobi5<false><<<g5, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, rows);
         } else {
             dim3 g4(cdiv(c->g.nz + 1, 128), cdiv(c->g.ny + 2, 4), cdiv(planes, kRows3));
             k3_jacobi4<<<g4, 128, 0, c->stream>>>(c->g, c->k, c->jac, c->p(), c->p_alt(), c->buf[B3_RHS], c->all_a, c->all_b, kRows3);

@@ -387,7 +387,7 @@ k3_jacobi(Grid3 g, Consts3 c, const float* __restrict__ p, float* __restrict__ p
 // One sweep, 4 consecutive k per lane (LDG.128 / STG.128), hoisted rhs.  Cells away from every wall use literal
 // coefficients and the exact reciprocal division (ConstDiv, verified at context creation); the rest (wall
 // rows / columns, ghosts) take the selected-coefficient IEEE path.  Same arithmetic, same order.
-struct Jac3C { float cx, cy, cz; ConstDiv dv; int fast_div_ok; };
+struct Jac3C { float cx, cy, cz; ConstDiv dv; int fast_div_ok; int bare_div_ok; };   // bare: no sub-normal fix-up needed (proven, see k_check_div_by_const)
 
 __global__ void __launch_bounds__(128)
 k3_jacobi4(Grid3 g, Consts3 c, Jac3C jc, const float* __restrict__ p, float* __restrict__ pn, const float* __restrict__ rhs,
@@ -466,7 +466,8 @@ k3_jacobi4(Grid3 g, Consts3 c, Jac3C jc, const float* __restrict__ p, float* __r
 // per warp (an, as) and per lane (af, ab); the constant-divisor quotient for every cell plus an IEEE division only on
 // the cells whose diagonal differs; one warp-level fix-up for sub-normal quotients; everything row i+1 needs is
 // requested while row i is computed; strips cover interior columns only (the lane next to a ghost column copies it).
-__global__ void __launch_bounds__(128, 7)      // 70 registers, 28 warps per SM: 512^3 step 7.14 -> 6.60 ms (6 blocks: 6.85, 8 blocks spill: 7.21)
+template <bool BARE>
+__global__ void __launch_bounds__(128, BARE ? 8 : 7)      // 28 (32) warps per SM: 512^3 step 7.14 -> 6.60 ms (6 blocks: 6.85, 8 blocks with the sub-normal path spill: 7.21)
 k3_jacobi5(Grid3 g, Consts3 c, Jac3C jc, const float* __restrict__ p, float* __restrict__ pn, const float* __restrict__ rhs,
            int r0, int r1, int rows_per_block) {
     const int lane = threadIdx.x & 31;
@@ -537,8 +538,9 @@ k3_jacobi5(Grid3 g, Consts3 c, Jac3C jc, const float* __restrict__ p, float* __r
             if (jc.fast_div_ok && !iw && !jw) {
                 bool slow = false;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) { r[q] = div_by_const_core(t[q], jc.dv.b, jc.dv.r); slow = slow || div_needs_ieee(t[q]); }
-                if (__any_sync(0xffffffffu, slow)) {                      // sub-normal quotients: the fp64 scheme
+                for (int q = 0; q < 4; ++q) { r[q] = div_by_const_core(t[q], jc.dv.b, jc.dv.r); slow = slow || (!BARE && div_needs_ieee(t[q])); }
+                if (!BARE && __any_sync(0xffffffffu, slow)) {             // sub-normal quotients: the fp64 scheme (not needed where the
+                                                                          // bare form is proven exact for every numerator: BARE)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) if (div_needs_ieee(t[q])) r[q] = div_slow(t[q], jc.dv);
                 }
