@@ -517,7 +517,9 @@ static int run_jacobi_sweep(VofCtx* c, int rhs_mode) {
     const int rpb = chunk_rows(c, rows, cdiv(c->g.ny + 2, 32), 4, 32);
     dim3 grid(cdiv(c->g.ny + 2, kBlockJ), cdiv(rows, rpb));
     const float* rhoF = rhs_mode == 2 ? c->F() : c->buf[BUF_RHO];
-#define JARGS c->g, c->k, c->p(), c->p_alt(), c->buf[BUF_RHS], rhoF, c->buf[BUF_US], c->buf[BUF_VS], c->all_a, c->all_b, rpb
+    const int bare = c->jac.bare_div_ok && c->opt_bare_div;
+#define JARGS c->g, c->k, c->p(), c->p_alt(), c->buf[BUF_RHS], rhoF, c->buf[BUF_US], c->buf[BUF_VS], c->all_a, c->all_b, rpb, \
+              c->jac.dv[0].b, c->jac.dv[0].r, c->jac.dv[1].b, c->jac.dv[1].r, bare
     if (rhs_mode == 0) k_jacobi<0><<<grid, kBlockJ, 0, c->stream>>>(JARGS);
     else if (rhs_mode == 1) k_jacobi<1><<<grid, kBlockJ, 0, c->stream>>>(JARGS);
     else k_jacobi<2><<<grid, kBlockJ, 0, c->stream>>>(JARGS);

@@ -125,7 +125,7 @@ template <int RHS_MODE>
 __global__ void __launch_bounds__(kBlockJ)
 k_jacobi(Grid g, Consts c, const float* __restrict__ p, float* __restrict__ pn,
          const float* __restrict__ rhs, const float* __restrict__ rhoF, const float* __restrict__ us,
-         const float* __restrict__ vs, int r0, int r1, int rows_per_block) {
+         const float* __restrict__ vs, int r0, int r1, int rows_per_block, float b0, float rcp0, float b1, float rcp1, int bare) {
     const int j = blockIdx.x * kBlockJ + threadIdx.x;
     if (j > g.ny + 1) return;
     const int ia = r0 + blockIdx.y * rows_per_block;
@@ -158,7 +158,14 @@ k_jacobi(Grid g, Consts c, const float* __restrict__ p, float* __restrict__ pn,
             t = t - aw * p_m;
             t = t - an * p[o + 1];
             t = t - as * p[o - 1];
-            out = div_nz(t, ap);                // p = 0 ahead of the pressure front: skip nvcc's slow path for 0 / ap
+            // bare: the context proved q = RN(t r), q' = fma(fma(-q, b, t), r, q) equal to t / b for every fp32 t and both
+            // interior-row diagonals (vof2d_create); rows next to an i-wall keep the IEEE division
+            if (bare && gi != 1 && gi != g.nx) {
+                const bool wj = j == 1 || j == g.ny;
+                const float b = wj ? b1 : b0, r = wj ? rcp1 : rcp0;
+                const float q = t * r;
+                out = __fmaf_rn(__fmaf_rn(-q, b, t), r, q);
+            } else out = div_nz(t, ap);         // p = 0 ahead of the pressure front: skip nvcc's slow path for 0 / ap
         }
         pn[o] = out;
         p_m = p_c; p_c = p_p; us_c = us_p;

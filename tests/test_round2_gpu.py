@@ -300,6 +300,7 @@ def test_async_field_read_does_not_block_and_is_a_snapshot(built_lib):
     s = VofSolver2D(scaled_params(4096)); s.set_init_F(3); s.run(10)
     want = s.F.to_numpy()
     out = _lib.pinned_empty(want.shape)
+    s.F.to_numpy_async(out); s.F.wait()              # the first call sets up the side stream and the device snapshot buffer
     s.synchronize()
     t0 = time.perf_counter()
     s.F.to_numpy_async(out)
