@@ -180,14 +180,16 @@ int64_t vof2d_launch_count(const VofCtx* c);
 int vof2d_profile(VofCtx* c, int enable);                 /* 0 off, 1 every launch, k > 1 the launches of every k-th vof2d_step; always resets the spans */
 int vof2d_profile_read(VofCtx* c, int kind, double* ms_total, int64_t* spans);  /* synchronous */
 
-/* tuning knobs for A/B measurements (defaults = fast paths; results are identical either way) */
+/* tuning knobs for A/B measurements (defaults = fast paths).  Results are identical either way -- except for the two opt-ins
+ * that say otherwise: VOF_OPT_PRESSURE_SOLVER = 1 and VOF_OPT_FAST_MATH = 1. */
 enum {
     VOF_OPT_JACOBI_TB = 0,    /* blocked Jacobi (several sweeps per HBM pass): 0 never, 1 from ~1800^2 up (default), 2 always */
     VOF_OPT_FCT_X_COLS = 1,   /* columns per lane of the x-sweep kernel: 2 (default) or 4 */
     VOF_OPT_ADVECT_COLS = 2,  /* columns per lane of the momentum predictor: 2 (default) or 4 */
     VOF_OPT_JACOBI_MAXT = 5,  /* sweeps per HBM pass of the blocked Jacobi at most: 0 (default) by grid size (3 up to ~5800^2,
                                  5 beyond), or 1 .. 5 */
-    VOF_OPT_JACOBI_ROWS = 7,  /* > 0: rows per work item of the blocked Jacobi (tuning; default 0 = max(16 T, 48)) */
+    VOF_OPT_JACOBI_ROWS = 7,  /* > 0: rows per work item of the blocked Jacobi (tuning; default 0 = max(16 T, 48) in the second generation,
+                                 the short items of the third: see VOF_OPT_JACOBI_LONG_PCT) */
     VOF_OPT_JACOBI_LONG_PCT = 8, /* third-generation Jacobi: percent of the rows cut into one long work item per resident warp (default 75;
                                   the rest becomes short items of VOF_OPT_JACOBI_ROWS rows, default max(8 T, 24)) */
     VOF_OPT_PRESSURE_SOLVER = 9, /* 0 (default): the reference's Jacobi sweeps (2dvof.py:236-266, 521-522); 1: the same number of
