@@ -608,7 +608,9 @@ static int launch_jacobi_tb(VofCtx* c, const float* pin, float* pout) {
     const int nitems = sc.nstrips * sc.nchunks;
     const int nwarps = std::min(nitems, c->jac_resident_warps[T]);
     CU(cudaMemsetAsync(sc.counter, 0, sizeof(unsigned int), c->stream));
-    kern<<<cdiv(nwarps, kJacWarpsPerBlock), 32 * kJacWarpsPerBlock, 0, c->stream>>>(c->g, c->jac, sc, pin, pout, c->buf[BUF_RHS],
+    JacTB jc = c->jac;
+    jc.bare_div_ok = jc.bare_div_ok && c->opt_bare_div;
+    kern<<<cdiv(nwarps, kJacWarpsPerBlock), 32 * kJacWarpsPerBlock, 0, c->stream>>>(c->g, jc, sc, pin, pout, c->buf[BUF_RHS],
                                                                                   c->in_a, c->in_b);
     return launch_ok("k_jacobi_tb");
 }

@@ -168,7 +168,10 @@ __device__ __forceinline__ void jac_step(JacPipe<T>& S, const JacEdge& E, const 
                 for (int k = 0; k < 4; ++k) {
                     const ConstDiv& d = jc.dv[EDGE ? E.cls[k] : 0];
                     out[k] = div_by_const_core(t[k], d.b, d.r);
-                    slow = slow || div_needs_ieee(t[k]);
+                }
+                if (!jc.bare_div_ok) {          // bare_div_ok: the three operations are proven exact for every numerator
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) slow = slow || div_needs_ieee(t[k]);
                 }
                 if (slow) {
 #pragma unroll
