@@ -621,13 +621,18 @@ static int launch_jacobi_tb(VofCtx* c, const float* pin, float* pout) {
 // hundred MB (short register pipelines: the device is not full and per-warp latency counts), 5 beyond (HBM traffic counts).
 // opt_jacobi_tb: 0 = never, 1 = by grid size (default), 2 = always.  opt_jacobi_maxt: 0 = by grid size (default), 1..5.
 static double jacobi_field_mb(const VofCtx* c) { return 3.0 * (double)c->g.nrows * c->g.pitch * sizeof(float) / 1e6; }   // p, p', rhs
+static bool packed_jacobi_eligible(const VofCtx* c) { return c->opt_jacobi_pk && c->jac.fast_div_ok && c->jac.cx == c->jac.cy; }
 static bool use_jacobi_tb(const VofCtx* c) {
     if (c->opt_jacobi_tb == 0) return false;
     if (c->opt_jacobi_tb == 2) return true;
-    return jacobi_field_mb(c) > 40.0;
+    // the packed kernel breaks even with ten single sweeps at ~1024^2 (0.089 ms both) and wins from there (1536^2: 0.089 vs 0.129)
+    return jacobi_field_mb(c) > (packed_jacobi_eligible(c) ? 15.0 : 40.0);
 }
 static int jacobi_max_sweeps(const VofCtx* c) {
     if (c->opt_jacobi_maxt > 0) return c->opt_jacobi_maxt;
+    // the packed kernel (96 registers, 20 warps per SM) has no short-pipeline advantage to lose: 5 sweeps per pass at every
+    // size it runs at (10 sweeps, 3 + 3 + 2 + 2 -> 5 + 5: 2048^2 0.111 -> 0.098 ms, 3072^2 0.148 -> 0.121, 4096^2 0.242 -> 0.146)
+    if (packed_jacobi_eligible(c)) return 5;
     return jacobi_field_mb(c) > 400.0 ? 5 : 3;
 }
 
