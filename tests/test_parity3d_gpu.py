@@ -123,6 +123,36 @@ def test_generations_identical_3d(built_lib):
         assert out[0][k].tobytes() == out[1][k].tobytes(), f"field {k} differs between the kernel generations"
 
 
+@pytest.mark.parametrize("shape", [(40, 12, 128), (21, 9, 150), (36, 7, 260), (5, 6, 8), (4, 4, 8), (9, 11, 130)])
+def test_multi_sweep_call_on_a_random_state_3d(built_lib, shape):
+    """`solve_p_jacobi(7)` -- hoisted rhs + seven launches of the second-generation 7-point sweep (k3_jacobi5; a single-sweep
+    call runs the first-generation kernel) -- on a random state with exact zeros in p, against 7 sweeps of the oracle
+    (3dvof.py:261-283): p with ghosts, every bit.  Shapes: full strips, a float4 straddling nz, three strips with a
+    4-column tail, tiny grids, and several plane chunks."""
+    nx, ny, nz = shape
+    rng = np.random.default_rng(11)
+    P = Vof3DParams(nx=nx, ny=ny, nz=nz, Lx=5e-4 * nx, Ly=5e-4 * ny, Lz=5e-4 * nz)
+    o = Vof3DOracle(P)
+    shp = o.F.shape
+    o.F[...] = rng.random(shp, dtype=np.float32)
+    for k in ("u_star", "v_star", "w_star"):
+        getattr(o, k)[...] = (rng.random(shp, dtype=np.float32) - 0.5) * 2.0
+    o.p[...] = (rng.random(shp, dtype=np.float32) - 0.5) * 100.0
+    o.p[1:-1, 1:-1, 1:-1][rng.random((nx, ny, nz)) < 0.3] = 0.0        # zero numerators and signed zeros on the way
+    init = {k: getattr(o, k).copy() for k in ("F", "u_star", "v_star", "w_star", "p")}
+    o.cal_nu_rho()
+    for _ in range(7):
+        o.solve_p_jacobi()
+    s = _solver(P)
+    for k, v in init.items():
+        getattr(s, k).from_numpy(v)
+    s.cal_nu_rho()
+    s.solve_p_jacobi(7)
+    got = s.p.to_numpy()
+    bad = np.argwhere(got.view(np.uint32) != o.p.view(np.uint32))
+    assert bad.size == 0, f"{len(bad)} cells of p differ from the oracle, first {bad[0]}: {got[tuple(bad[0])]} vs {o.p[tuple(bad[0])]}"
+
+
 def test_lean_bc_tracks_outside_writers_3d(built_lib):
     """The fused 3-D step skips set_BC on fields whose interior has not changed since their ghosts were filled; any writer
     other than a whole step (field_set, single entries) must bring the full calls back.  Interleave both with the oracle."""
