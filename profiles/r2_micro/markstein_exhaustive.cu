@@ -28,10 +28,12 @@ int main() {
     unsigned long long *bad, *badt; unsigned int* first;
     cudaMallocManaged(&bad, 8); cudaMallocManaged(&badt, 8); cudaMallocManaged(&first, 4);
     // dx as the library derives it: difference of two fp32 node coordinates, L = 0.1 * n / 200 (scaled) or 0.1 (reference 200^2)
-    const int ns[] = {200, 2048, 8192, 32768};
-    for (int n : ns) {
-        const double L = 0.1 * n / 200;
-        const float x3 = (float)(L * 2 / n), x2 = (float)(L * 1 / n);
+    // constant-dx scaling (L = 0.1 n / 200) and, last, BASELINE config 2: 2048^2 with the reference's L = 0.1
+    const int ns[] = {200, 2048, 8192, 32768, -2048};
+    for (int n0 : ns) {
+        const int n = n0 < 0 ? -n0 : n0;
+        const double L = n0 < 0 ? 0.1 : 0.1 * n / 200;
+        const float x3 = (float)(L * 2 / n), x2 = (float)(L * 1 / n);      // np.linspace(0, L, n + 1)[2], [1] in fp32
         const double dx = (double)x3 - (double)x2;
         for (int wi = 0; wi < 2; ++wi) for (int wj = 0; wj < 2; ++wj) {
             const float b = diag(dx, wi, wj), r = 1.0f / b;
