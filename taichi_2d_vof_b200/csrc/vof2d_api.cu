@@ -910,12 +910,14 @@ static bool tile_geometry(const VofCtx* c, TileArgs* a, dim3* grid, size_t* smem
     const int tj = kTileW - 2 * H;
     if (tj < 8) return false;
     const int max_th = (int)((227 * 1024) / (10 * kTileW * sizeof(float) + kTileW));   // ten tile arrays + one class byte per cell
-    const int bj = cdiv(c->g.ny + 2, tj);
+    int bj = cdiv(c->g.ny + 2, tj);
+    if (c->g.ny + 2 - (bj - 1) * tj == 1 && bj > 1) --bj;                          // the far ghost column goes with column ny (see k_step_tile)
     int bi = std::max(1, c->sm_count / bj);                                         // about one block per SM ...
     int ti = cdiv(c->g.nx + 2, bi);
     ti = std::max(4, std::min(ti, max_th - 2 * H));                                 // ... as long as the tile fits
     if (ti + 2 * H > max_th) return false;
     bi = cdiv(c->g.nx + 2, ti);
+    if (c->g.nx + 2 - (bi - 1) * ti == 1 && bi > 1) --bi;                          // the far ghost row goes with row nx
     // by grid size: the tile kernel wins while its blocks are one wave (200^2 2.1x ... 512^2 1.4x); with a second wave
     // the redundant halo work costs more than the launches save (640^2: 0.8x) -- profiles/exp_tile.py
     if (c->opt_tile == 1 && (long long)bi * bj > c->sm_count) return false;

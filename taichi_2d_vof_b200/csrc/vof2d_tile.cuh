@@ -75,7 +75,13 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
     m.us = m.FB + cells; m.vs = m.us + cells; m.kap = m.vs + cells; m.rhs = m.kap + cells;
     unsigned char* cls = reinterpret_cast<unsigned char*>(m.rhs + cells);
     const int oi0 = blockIdx.y * a.ti, oj0 = blockIdx.x * a.tj;                  // first owned cell
-    const int oi1 = min(oi0 + a.ti - 1, nx + 1), oj1 = min(oj0 + a.tj - 1, ny + 1);
+    int oi1 = min(oi0 + a.ti - 1, nx + 1), oj1 = min(oj0 + a.tj - 1, ny + 1);
+    // A block never owns the far ghost row / column alone: F, p, u, v there are set_BC copies of row nx / column ny, whose own
+    // dependency radius H would then reach one cell beyond the tile.  The block that owns row nx (column ny) owns the
+    // ghost line next to it as well (the host launches no block for it, tile_geometry); nothing exists beyond it, so the
+    // tile still covers everything its owned cells depend on.
+    if (oi1 == nx) oi1 = nx + 1;
+    if (oj1 == ny) oj1 = ny + 1;
     const int gi0 = oi0 - H, gj0 = oj0 - H;                                      // global index of tile cell (0, 0)
     // a cell takes part in a phase when its stencil (radius r) lies inside the tile array
     auto inside = [&](int li, int lj, int r) { return li >= r && li < th - r && lj >= r && lj < kTileW - r; };

@@ -55,7 +55,10 @@ def _live_state(nx, ny, seed, vel_scale, P):
 
 
 @pytest.mark.parametrize("shape,n_jacobi,seed", [((97, 131), 10, 1), ((64, 35), 10, 2), ((150, 70), 2, 3), ((33, 140), 13, 4),
-                                                 ((200, 200), 7, 5)])
+                                                 ((200, 200), 7, 5),
+                                                 # the far ghost row / column would be a block's only owned line (65 = 16 * 4 + 1 rows,
+                                                 # 69 = 2 * 34 + 1 and 103 = 3 * 34 + 1 columns): it goes with row nx / column ny
+                                                 ((63, 67), 10, 6), ((50, 101), 10, 7)])
 def test_tile_step_on_live_states_equals_oracle(built_lib, shape, n_jacobi, seed):
     nx, ny = shape
     P = Vof2DParams(nx=nx, ny=ny, Lx=0.1 * nx / 200, Ly=0.1 * ny / 200, n_jacobi=n_jacobi)
