@@ -65,6 +65,11 @@ __device__ __forceinline__ void tile_for(int th, Fn fn) {       // the tile's ce
     for (int c = threadIdx.x; c < ncell; c += kTileThreads) fn(c);
 }
 
+template <class Fn>
+__device__ __forceinline__ void tile_rows(int r0, int r1, Fn fn) {   // the cells of tile rows r0 .. r1: 16 rows per pass, a thread keeps its column
+    for (int li = r0 + (int)(threadIdx.x >> 6); li <= r1; li += kTileThreads / kTileW) fn(li * kTileW + (int)(threadIdx.x & 63));
+}
+
 __global__ void __launch_bounds__(kTileThreads, 1)
 k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
     extern __shared__ __align__(16) float tile_smem[];
@@ -85,6 +90,14 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
     const int gi0 = oi0 - H, gj0 = oj0 - H;                                      // global index of tile cell (0, 0)
     // a cell takes part in a phase when its stencil (radius r) lies inside the tile array
     auto inside = [&](int li, int lj, int r) { return li >= r && li < th - r && lj >= r && lj < kTileW - r; };
+    // Late phases run on the rows that can still reach an owned cell: `within(m, fn)` = the owned rows and m rows either side.
+    // Margins, backwards from the write-back (0): final set_BC column loop 0 / row loop 1, post-process 1, second FCT sweep
+    // 1 / 2 / 3 (loops 3+4, 2, 1: each reads its predecessor one cell further out; across the sweep direction the limiter
+    // ratios of the neighbours), first sweep 4 / 5 / 5, so F, u, v are needed 5 rows out after set_BC (525): its column
+    // loop 5, row loop 6, projection 6, Jacobi sweep s (of n) 7 + (n - 1 - s).  The margins are those of the sweep order
+    // that needs more (second sweep along i); rows further out hold garbage either way -- what the halo is for.
+    const int own_r0 = H, own_r1 = H + (oi1 - oi0);
+    auto within = [&](int mi, auto fn) { tile_rows(max(0, own_r0 - mi), min(th - 1, own_r1 + mi), fn); };
 
     // ---- load the old state (cells outside the field do not exist: never read by a cell inside a loop range)
     tile_for(th, [&](int c) {
@@ -192,8 +205,8 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
     __syncthreads();
 
     // set_BC (162-189) on the tile: the row loop, a barrier, the column loop; u, v, F, p (rho is taken from F).
-    auto set_bc = [&]() {
-        tile_for(th, [&](int c) {
+    auto set_bc = [&](int mi) {                  // mi: rows needed afterwards (the row loop runs one row further out)
+        within(mi + 1, [&](int c) {
             const int li = c >> 6, lj = c & 63;
             const int gi = gi0 + li, gj = gj0 + lj;
             if (gi < 0 || gi > nx + 1) return;
@@ -207,7 +220,7 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
             }
         });
         __syncthreads();
-        tile_for(th, [&](int c) {
+        within(mi, [&](int c) {
             const int li = c >> 6, lj = c & 63;
             const int gi = gi0 + li, gj = gj0 + lj;
             if (gj < 0 || gj > ny + 1) return;
@@ -222,7 +235,7 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
         });
         __syncthreads();
     };
-    set_bc();                                                                    // 518
+    set_bc(th);                                                                  // 518: the whole tile
 
     // ---- solve_p_jacobi x n (236-266, 521-522): rhs once (its value is the same in every sweep), then the sweeps
     tile_for(th, [&](int c) {
@@ -234,7 +247,7 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
     __syncthreads();
     float* pc = m.p; float* pn = m.pB;
     for (int s = 0; s < a.n_jacobi; ++s) {
-        tile_for(th, [&](int c) {
+        within(7 + (a.n_jacobi - 1 - s), [&](int c) {
             const unsigned q = cls[c];
             if (!(q & T_IN)) return;
             const float b = m.rhs[c];
@@ -266,7 +279,7 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
 
     // ---- update_uv (269-280), Courant offenders counted over the owned cells
     unsigned flags = 0;
-    tile_for(th, [&](int c) {
+    within(6, [&](int c) {
         const unsigned q = cls[c];
         if (!(q & T_IN)) return;
         const bool own = (q & T_OWN) != 0;
@@ -287,10 +300,10 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
     if (flags) atomicAdd(a.courant_count, (unsigned long long)flags);
     __syncthreads();
     if (pc != m.p) {                          // keep the pressure in m.p: set_bc and the write-back address it there
-        tile_for(th, [&](int c) { m.p[c] = pc[c]; });
+        within(7, [&](int c) { m.p[c] = pc[c]; });
         __syncthreads();
     }
-    set_bc();                                                                    // 525
+    set_bc(5);                                                                   // 525
 
     // ---- solve_VOF_rudman (312-318): two FCT sweeps (321-448), order by the step's parity.
     // Scratch: Ftd -> rhs, rp -> kap, rm -> pB.  Never-written entries of Ftd, rp, rm, cx, cy are 0.
@@ -301,7 +314,8 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
         const int sd = along_x ? kTileW : 1, so = along_x ? 1 : kTileW;      // cell strides along / across the sweep
         const float* vel = along_x ? m.u : m.v;
         const float dtd = along_x ? k.dtdy : k.dtdx;
-        tile_for(th, [&](int c) {          // loop 1: the transported-diffused value
+        const int m3 = half == 0 ? 4 : 1;  // rows this sweep's result is needed on beyond the owned ones
+        within(half == 0 ? 5 : 3, [&](int c) {   // loop 1: the transported-diffused value
             Ftd[c] = 0.0f; rp[c] = 0.0f; rm[c] = 0.0f;
             if (!(cls[c] & T_IN)) return;
             const float vc = vel[c], vp = vel[c + sd];
@@ -315,7 +329,7 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
             Ftd[c] = t;
         });
         __syncthreads();
-        tile_for(th, [&](int c) {          // loop 2: limiter ratios
+        within(m3 + 1, [&](int c) {        // loop 2: limiter ratios
             if (!(cls[c] & T_IN)) return;
             const float t_c = Ftd[c], t_m = Ftd[c - sd], t_p = Ftd[c + sd];
             const float fmax = fmaxf(fmaxf(t_c, t_m), t_p), fmin = fminf(fminf(t_c, t_m), t_p);
@@ -335,7 +349,7 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
             rm[c] = pm > 0.0f ? fminf(1.0f, div_nz(qm, pm)) : 0.0f;
         });
         __syncthreads();
-        tile_for(th, [&](int c) {          // loops 3 + 4: face limiters and the corrective update
+        within(m3, [&](int c) {            // loops 3 + 4: face limiters and the corrective update
             Fo[c] = Fc[c];                                // ghost cells keep their value through a sweep
             const unsigned q = cls[c];
             if (!(q & T_IN)) return;
@@ -376,12 +390,12 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
         float* sw = Fc; Fc = Fo; Fo = sw;
     }
     // two sweeps: the new F is back in m.F.  post_process_f (452-455) on every cell, then set_BC (528)
-    tile_for(th, [&](int c) { m.F[c] = var3(m.F[c], 0.0f, 1.0f); });
+    within(1, [&](int c) { m.F[c] = var3(m.F[c], 0.0f, 1.0f); });
     __syncthreads();
-    set_bc();
+    set_bc(0);
 
     // ---- write back the owned cells
-    tile_for(th, [&](int c) {
+    within(0, [&](int c) {
         if (!(cls[c] & T_OWN)) return;
         const size_t o = (size_t)(gi0 + (c >> 6)) * P + gj0 + (c & 63);
         a.un[o] = m.u[c]; a.vn[o] = m.v[c]; a.pn[o] = m.p[c]; a.Fn[o] = m.F[c];
