@@ -96,8 +96,20 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
     // ratios of the neighbours), first sweep 4 / 5 / 5, so F, u, v are needed 5 rows out after set_BC (525): its column
     // loop 5, row loop 6, projection 6, Jacobi sweep s (of n) 7 + (n - 1 - s).  The margins are those of the sweep order
     // that needs more (second sweep along i); rows further out hold garbage either way -- what the halo is for.
-    const int own_r0 = H, own_r1 = H + (oi1 - oi0);
+    const int own_r0 = H, own_r1 = H + (oi1 - oi0), own_c0 = H, own_c1 = H + (oj1 - oj0);
     auto within = [&](int mi, auto fn) { tile_rows(max(0, own_r0 - mi), min(th - 1, own_r1 + mi), fn); };
+    // The phases after the sweeps are few cells with long expressions: the same margins along j as well, and the cells of the
+    // rectangle dealt out compactly (cell = idx / w, idx % w through one multiplication: exact for idx < 2^13, w <= 64) --
+    // at 200^2 the 19 x 44 cells of the first FCT sweep are one pass of the block instead of two.
+    auto within2 = [&](int mi, int mj, auto fn) {
+        const int r0 = max(0, own_r0 - mi), r1 = min(th - 1, own_r1 + mi), c0 = max(0, own_c0 - mj), c1 = min(kTileW - 1, own_c1 + mj);
+        const int w = c1 - c0 + 1, n = (r1 - r0 + 1) * w;
+        const float rw = 1.0f / (float)w;
+        for (int idx = threadIdx.x; idx < n; idx += kTileThreads) {
+            const int q = (int)(((float)idx + 0.5f) * rw);
+            fn((r0 + q) * kTileW + c0 + (idx - q * w));
+        }
+    };
 
     // ---- load the old state (cells outside the field do not exist: never read by a cell inside a loop range)
     tile_for(th, [&](int c) {
@@ -205,8 +217,8 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
     __syncthreads();
 
     // set_BC (162-189) on the tile: the row loop, a barrier, the column loop; u, v, F, p (rho is taken from F).
-    auto set_bc = [&](int mi) {                  // mi: rows needed afterwards (the row loop runs one row further out)
-        within(mi + 1, [&](int c) {
+    auto set_bc = [&](int mi) {                  // mi: rows / columns needed afterwards (the row loop runs one row further out)
+        within2(mi + 1, mi, [&](int c) {
             const int li = c >> 6, lj = c & 63;
             const int gi = gi0 + li, gj = gj0 + lj;
             if (gi < 0 || gi > nx + 1) return;
@@ -220,7 +232,7 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
             }
         });
         __syncthreads();
-        within(mi, [&](int c) {
+        within2(mi, mi, [&](int c) {
             const int li = c >> 6, lj = c & 63;
             const int gi = gi0 + li, gj = gj0 + lj;
             if (gj < 0 || gj > ny + 1) return;
@@ -247,7 +259,7 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
     __syncthreads();
     float* pc = m.p; float* pn = m.pB;
     for (int s = 0; s < a.n_jacobi; ++s) {
-        within(7 + (a.n_jacobi - 1 - s), [&](int c) {
+        auto sweep = [&](int c) {
             const unsigned q = cls[c];
             if (!(q & T_IN)) return;
             const float b = m.rhs[c];
@@ -271,7 +283,12 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
                 out = (!wi) ? tdiv_ap(t, a.d_ap1, a.fast, a.bare) : div_nz(t, ap);
             }
             pn[c] = out;
-        });
+        };
+        // the new u, v are needed 5 cells out (the FCT sweeps; set_BC reaches inwards, never outwards), and so is the last
+        // sweep's p (the projection's p[i-1] of the lowest needed u row is the row above it); each earlier sweep one more.
+        // The last sweeps are few enough cells for the compact rectangle (one pass instead of two at 200^2).
+        const int mg = 5 + (a.n_jacobi - 1 - s);
+        if (mg <= 6) within2(mg, mg, sweep); else within(mg, sweep);
         __syncthreads();
         float* sw = pc; pc = pn; pn = sw;
     }
@@ -279,7 +296,7 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
 
     // ---- update_uv (269-280), Courant offenders counted over the owned cells
     unsigned flags = 0;
-    within(6, [&](int c) {
+    within2(6, 6, [&](int c) {
         const unsigned q = cls[c];
         if (!(q & T_IN)) return;
         const bool own = (q & T_OWN) != 0;
@@ -300,7 +317,7 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
     if (flags) atomicAdd(a.courant_count, (unsigned long long)flags);
     __syncthreads();
     if (pc != m.p) {                          // keep the pressure in m.p: set_bc and the write-back address it there
-        within(7, [&](int c) { m.p[c] = pc[c]; });
+        within2(7, 7, [&](int c) { m.p[c] = pc[c]; });
         __syncthreads();
     }
     set_bc(5);                                                                   // 525
@@ -314,8 +331,9 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
         const int sd = along_x ? kTileW : 1, so = along_x ? 1 : kTileW;      // cell strides along / across the sweep
         const float* vel = along_x ? m.u : m.v;
         const float dtd = along_x ? k.dtdy : k.dtdx;
-        const int m3 = half == 0 ? 4 : 1;  // rows this sweep's result is needed on beyond the owned ones
-        within(half == 0 ? 5 : 3, [&](int c) {   // loop 1: the transported-diffused value
+        const int m3 = half == 0 ? 4 : 1;  // rows / columns this sweep's result is needed on beyond the owned ones
+        const int m1 = half == 0 ? 5 : 3;
+        within2(m1, m1, [&](int c) {       // loop 1: the transported-diffused value
             Ftd[c] = 0.0f; rp[c] = 0.0f; rm[c] = 0.0f;
             if (!(cls[c] & T_IN)) return;
             const float vc = vel[c], vp = vel[c + sd];
@@ -329,7 +347,7 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
             Ftd[c] = t;
         });
         __syncthreads();
-        within(m3 + 1, [&](int c) {        // loop 2: limiter ratios
+        within2(m3 + 1, m3 + 1, [&](int c) {   // loop 2: limiter ratios
             if (!(cls[c] & T_IN)) return;
             const float t_c = Ftd[c], t_m = Ftd[c - sd], t_p = Ftd[c + sd];
             const float fmax = fmaxf(fmaxf(t_c, t_m), t_p), fmin = fminf(fminf(t_c, t_m), t_p);
@@ -349,7 +367,7 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
             rm[c] = pm > 0.0f ? fminf(1.0f, div_nz(qm, pm)) : 0.0f;
         });
         __syncthreads();
-        within(m3, [&](int c) {            // loops 3 + 4: face limiters and the corrective update
+        within2(m3, m3, [&](int c) {       // loops 3 + 4: face limiters and the corrective update
             Fo[c] = Fc[c];                                // ghost cells keep their value through a sweep
             const unsigned q = cls[c];
             if (!(q & T_IN)) return;
@@ -390,12 +408,12 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
         float* sw = Fc; Fc = Fo; Fo = sw;
     }
     // two sweeps: the new F is back in m.F.  post_process_f (452-455) on every cell, then set_BC (528)
-    within(1, [&](int c) { m.F[c] = var3(m.F[c], 0.0f, 1.0f); });
+    within2(1, 1, [&](int c) { m.F[c] = var3(m.F[c], 0.0f, 1.0f); });
     __syncthreads();
     set_bc(0);
 
     // ---- write back the owned cells
-    within(0, [&](int c) {
+    within2(0, 0, [&](int c) {
         if (!(cls[c] & T_OWN)) return;
         const size_t o = (size_t)(gi0 + (c >> 6)) * P + gj0 + (c & 63);
         a.un[o] = m.u[c]; a.vn[o] = m.v[c]; a.pn[o] = m.p[c]; a.Fn[o] = m.F[c];
