@@ -284,9 +284,12 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
             }
             pn[c] = out;
         };
-        // the new u, v are needed 5 cells out (the FCT sweeps; set_BC reaches inwards, never outwards), and so is the last
-        // sweep's p (the projection's p[i-1] of the lowest needed u row is the row above it); each earlier sweep one more.
-        // The last sweeps are few enough cells for the compact rectangle (one pass instead of two at 200^2).
+        // The FCT sweeps read the new u, v at most 3 cells beyond the owned ones (u[i-2 .. i+3], 2dvof.py:323-369; the
+        // cross-direction limiter ratios, multiplied by 0.0, one further: they only have to be finite), set_BC copies
+        // inwards; the regions of the later phases are the conservative chain (5 / 6).  The last sweep's p is therefore
+        // needed at most 5 cells out, each earlier sweep's one more; what the projection reads further out is one sweep
+        // behind (finite) and feeds no needed cell.  The last sweeps are few enough cells for the compact rectangle
+        // (one pass of the block instead of two at 200^2).
         const int mg = 5 + (a.n_jacobi - 1 - s);
         if (mg <= 6) within2(mg, mg, sweep); else within(mg, sweep);
         __syncthreads();
