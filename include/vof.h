@@ -128,8 +128,12 @@ int vof2d_step_host(VofCtx* c, int istep, unsigned flags,
 /* ---- streamed host-buffer step (new): the state stays in HOST memory; the domain is cut into `n_slabs`
  * row slabs (deep halo, as for multi-GPU) and upload of slab s+1, the step of slab s and download of slab
  * s-1 overlap on three streams.  Same result as vof2d_step_host, bit for bit.  `p` are full-domain params.
- * The arrays are dense (nx+2)*(ny+2) floats; *_out may alias *_in (in-place).  Pinned host memory is
- * needed for the overlap (pageable memory works, serialised by the driver).  Synchronous.
+ * The arrays are dense (nx+2)*(ny+2) floats; *_out may alias *_in (in-place: a slab's download then waits
+ * for the next slab's upload of the rows it overwrites; with separate output arrays it does not, which
+ * shortens the pipeline's tail by one slab's transfer).  Pinned host memory is needed for the overlap
+ * (pageable memory works, serialised by the driver).  The PCIe copies are contiguous: they go through dense
+ * staging blocks on the device (8 more floats per cell, counted in vof2d_streamer_info's device_bytes;
+ * without room for them the copies are pitched and direct).  Synchronous.
  * Replaces the to_numpy()/from_numpy() round trip a host-resident caller of the reference pays
  * (2dvof.py:535, 565) around 2dvof.py:513-528. */
 typedef struct VofStreamer VofStreamer;
