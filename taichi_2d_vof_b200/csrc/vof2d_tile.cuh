@@ -94,8 +94,8 @@ k_step_tile(Grid g, Consts k, JacTB jc, TileArgs a) {
     // Margins, backwards from the write-back (0): final set_BC column loop 0 / row loop 1, post-process 1, second FCT sweep
     // 1 / 2 / 3 (loops 3+4, 2, 1: each reads its predecessor one cell further out; across the sweep direction the limiter
     // ratios of the neighbours), first sweep 4 / 5 / 5, so F, u, v are needed 5 rows out after set_BC (525): its column
-    // loop 5, row loop 6, projection 6, Jacobi sweep s (of n) 7 + (n - 1 - s).  The margins are those of the sweep order
-    // that needs more (second sweep along i); rows further out hold garbage either way -- what the halo is for.
+    // loop 5, row loop 6, projection 6, Jacobi sweep s (of n) 5 + (n - 1 - s) (see there).  The margins are those of the
+    // sweep order that needs more (second sweep along i); rows further out hold garbage either way -- what the halo is for.
     const int own_r0 = H, own_r1 = H + (oi1 - oi0), own_c0 = H, own_c1 = H + (oj1 - oj0);
     auto within = [&](int mi, auto fn) { tile_rows(max(0, own_r0 - mi), min(th - 1, own_r1 + mi), fn); };
     // The phases after the sweeps are few cells with long expressions: the same margins along j as well, and the cells of the
